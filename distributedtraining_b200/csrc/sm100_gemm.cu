@@ -1,0 +1,442 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a (bf16 in, fp32 accumulate in TMEM).
+//
+//   C[M,N] (+)= epilogue( A · B^T )        reduction dimension K
+//
+// * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring
+// * one elected thread issues tcgen05.mma (UMMA 128 x 256 x 16, cta_group::1), accumulators live in TMEM,
+//   double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of tile i+1
+// * epilogue warps read TMEM with tcgen05.ld, apply the fused epilogue (bias / GELU / residual / dGELU),
+//   stage through swizzled shared memory and leave via TMA store (bf16) or TMA reduce-add (fp32, split-K wgrad)
+// * both operand majors are supported so forward (A,B K-major), dgrad (B MN-major) and wgrad (A,B MN-major)
+//   run without any transposes.
+//
+// Role parity: replaces the cuBLAS GEMMs behind the reference's HF GPT-2 forward/backward
+// (reference hivetrain/training_manager.py:380-386).
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "sm100_ptx.cuh"
+
+namespace dtb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;   // one 128B swizzle atom of bf16
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSlabBytes = BLOCK_M * 128;       // 16 KB: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
+constexpr int kNumSlabBufs = 2;
+constexpr int kTmemCols = 512;
+constexpr int kNumThreads = 192;                // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNumSlabBufs * kSlabBytes + BLOCK_N * 4 /*bias*/ + 256 /*barriers*/;
+
+enum Epi : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_RESID = 3, EPI_DGELU = 4, EPI_RESID = 5 };
+
+struct GemmParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  CUtensorMap tmap_c;
+  CUtensorMap tmap_c2;  // second output (pre-activation) for EPI_BIAS_GELU
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, num_kb;
+  int epi;
+  int ldaux;
+  const __nv_bfloat16* bias;  // [N]
+  const __nv_bfloat16* aux;   // [M, ldaux]
+  float alpha;
+};
+
+DTB_DEVICE float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.f + t);
+}
+DTB_DEVICE float dgelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float x2 = x * x;
+  float u = k0 * (x + k1 * x * x2);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  float du = k0 * (1.f + 3.f * k1 * x2);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+}
+DTB_DEVICE uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+template <bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_ab = smem;
+  uint8_t* smem_slab = smem + kStages * kStageBytes;
+  float* smem_bias = reinterpret_cast<float*>(smem_slab + kNumSlabBufs * kSlabBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BLOCK_N);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const uint32_t warp_idx = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    tma_prefetch_desc(&p.tmap_c);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_t = w % p.tiles_n;
+        const int m_t = (w / p.tiles_n) % p.tiles_m;
+        const int sp = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem_ab + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
+          } else {
+            tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), &p.tmap_b, &full_bar[stage], n0 + a * 64, k0);
+          } else {
+            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], k0, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M, BLOCK_N);
+    // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 64-element atoms along MN are
+    // BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
+    constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
+    constexpr uint32_t a_kadv = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;  // descriptor start-address units (16 B)
+    constexpr uint32_t b_kadv = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int sp = w / (p.tiles_n * p.tiles_m);
+      const int kb0 = sp * p.kb_per_split;
+      const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const uint32_t quad = warp_idx & 3;              // TMEM lane quadrant this warp may access
+    const uint32_t row_l = quad * 32 + lane;         // row within the tile
+    const uint32_t epi_tid = threadIdx.x - 64;       // 0..127
+    const bool issuer = (epi_tid == 0);
+    uint32_t acc = 0, acc_phase = 0;
+    uint32_t slab_ctr = 0;
+    constexpr int kColsPerSlab = OUT_F32 ? 32 : 64;
+    constexpr int kSlabs = BLOCK_N / kColsPerSlab;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int n_t = w % p.tiles_n;
+      const int m_t = (w / p.tiles_n) % p.tiles_m;
+      const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
+      const int row = m0 + row_l;
+      const bool row_ok = row < p.M;
+      const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
+      if (has_bias) {
+        named_bar_sync(2, kEpiThreads);  // previous tile's readers of smem_bias are done
+        for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) {
+          int c = n0 + i;
+          smem_bias[i] = (c < p.N) ? __bfloat162float(p.bias[c]) : 0.f;
+        }
+        named_bar_sync(2, kEpiThreads);
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + acc * BLOCK_N + ((quad * 32u) << 16);
+#pragma unroll 1
+      for (int s = 0; s < kSlabs; ++s) {
+        const int c0 = s * kColsPerSlab;  // column offset inside the tile
+        if constexpr (OUT_F32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr_row + c0, r);
+          tmem_ld_wait();
+          if (s == kSlabs - 1) {  // accumulator fully drained -> hand TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          uint8_t* buf = smem_slab + (slab_ctr & 1) * kSlabBytes;
+          if (issuer) tma_store_wait_read<1>();
+          named_bar_sync(1, kEpiThreads);
+          uint8_t* rowp = buf + row_l * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float4 v;
+            v.x = __uint_as_float(r[ch * 4 + 0]) * p.alpha;
+            v.y = __uint_as_float(r[ch * 4 + 1]) * p.alpha;
+            v.z = __uint_as_float(r[ch * 4 + 2]) * p.alpha;
+            v.w = __uint_as_float(r[ch * 4 + 3]) * p.alpha;
+            *reinterpret_cast<float4*>(rowp + ((ch ^ (row_l & 7)) << 4)) = v;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (issuer) {
+            if (n0 + c0 < p.N) tma_reduce_add_2d(&p.tmap_c, buf, n0 + c0, m0);
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        } else {
+          uint32_t r[64];
+          tmem_ld_32x32b_x32(taddr_row + c0, r);
+          tmem_ld_32x32b_x32(taddr_row + c0 + 32, r + 32);
+          tmem_ld_wait();
+          if (s == kSlabs - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const bool dual = (p.epi == EPI_BIAS_GELU);
+          uint8_t* buf = smem_slab + (dual ? 0 : (slab_ctr & 1)) * kSlabBytes;
+          uint8_t* buf2 = smem_slab + kSlabBytes;
+          if (issuer) {
+            if (dual) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          named_bar_sync(1, kEpiThreads);
+          uint8_t* rowp = buf + row_l * 128;
+          uint8_t* rowp2 = buf2 + row_l * 128;
+          const int gcol0 = n0 + c0;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch * 8 + i]) * p.alpha;
+            if (has_bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8 + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU) {
+              float a[8];
+              const int gc = gcol0 + ch * 8;
+              if (row_ok && gc < p.N) {
+                const uint4 q = *reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + gc);
+                float2 f;
+                f = unpack_bf16x2(q.x); a[0] = f.x; a[1] = f.y;
+                f = unpack_bf16x2(q.y); a[2] = f.x; a[3] = f.y;
+                f = unpack_bf16x2(q.z); a[4] = f.x; a[5] = f.y;
+                f = unpack_bf16x2(q.w); a[6] = f.x; a[7] = f.y;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = 0.f;
+              }
+              if (p.epi == EPI_DGELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= dgelu_tanh_f(a[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += a[i];
+              }
+            }
+            const uint32_t sw = ((ch ^ (row_l & 7)) << 4);
+            if (dual) {
+              uint4 o2;
+              o2.x = pack_bf16x2(v[0], v[1]); o2.y = pack_bf16x2(v[2], v[3]);
+              o2.z = pack_bf16x2(v[4], v[5]); o2.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(rowp2 + sw) = o2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_f(v[i]);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(rowp + sw) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (issuer) {
+            if (gcol0 < p.N) {
+              tma_store_2d(&p.tmap_c, buf, gcol0, m0);
+              if (dual) tma_store_2d(&p.tmap_c2, buf2, gcol0, m0);
+            }
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D row-major tensor [outer, inner] with `pitch` elements between rows; box = [box_outer, box_inner]; 128B swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                 uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * uint64_t(elem_bytes)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                           : (elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : int(r);
+}
+
+template <bool A_MN, bool B_MN, bool OUT_F32>
+static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace dtb
+
+// C ABI.  A: K-major => [M, K] pitch lda; MN-major => [K, M] pitch lda.  B likewise with N.  C: [M, N] pitch ldc.
+// out_f32 => C is fp32 and the tile is reduce-ADDED into it (caller zeroes C); splits > 1 requires out_f32.
+extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                             int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
+                             float alpha, int splits, int num_sms, cudaStream_t stream) {
+  using namespace dtb;
+  GemmParams p;
+  int rc = 0;
+  if (a_mn) rc |= make_tmap_2d(&p.tmap_a, a, 2, M, K, lda, 64, BLOCK_K);
+  else      rc |= make_tmap_2d(&p.tmap_a, a, 2, K, M, lda, BLOCK_K, BLOCK_M);
+  if (b_mn) rc |= make_tmap_2d(&p.tmap_b, b, 2, N, K, ldb, 64, BLOCK_K);
+  else      rc |= make_tmap_2d(&p.tmap_b, b, 2, K, N, ldb, BLOCK_K, BLOCK_N);
+  if (out_f32) rc |= make_tmap_2d(&p.tmap_c, c, 4, N, M, ldc, 32, BLOCK_M);
+  else         rc |= make_tmap_2d(&p.tmap_c, c, 2, N, M, ldc, 64, BLOCK_M);
+  if (c2) rc |= make_tmap_2d(&p.tmap_c2, c2, 2, N, M, ldc2, 64, BLOCK_M);
+  else    p.tmap_c2 = p.tmap_c;
+  if (rc) return 1000 + rc;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits < 1) splits = 1;
+  if (!out_f32) splits = 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.epi = epi;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+  p.ldaux = ldaux;
+  p.alpha = alpha;
+  int total = p.tiles_m * p.tiles_n * p.splits;
+  int grid = total < num_sms ? total : num_sms;
+  if (grid < 1) return 0;
+  cudaError_t e;
+  if (out_f32) {
+    if (a_mn && b_mn) e = launch<true, true, true>(p, grid, stream);
+    else if (!a_mn && b_mn) e = launch<false, true, true>(p, grid, stream);
+    else if (!a_mn && !b_mn) e = launch<false, false, true>(p, grid, stream);
+    else e = launch<true, false, true>(p, grid, stream);
+  } else {
+    if (a_mn && b_mn) e = launch<true, true, false>(p, grid, stream);
+    else if (!a_mn && b_mn) e = launch<false, true, false>(p, grid, stream);
+    else if (!a_mn && !b_mn) e = launch<false, false, false>(p, grid, stream);
+    else e = launch<true, false, false>(p, grid, stream);
+  }
+  return e == cudaSuccess ? 0 : int(e);
+}

@@ -1,0 +1,430 @@
+"""Decoder-only transformer family (GPT-2 and Llama shapes) on flat arenas.
+
+Two implementations of the same maths:
+
+* :func:`oracle_loss` -- straightforward autograd PyTorch over views of a flat fp32 parameter vector.  It is the
+  numerical oracle for everything else and the CPU path of the simulation (``Local*``) roles.
+* :class:`TransformerEngine` -- explicit forward / backward over static buffers calling :mod:`distributedtraining_b200.ops`
+  (hand-written sm_100a kernels on a B200, the PyTorch reference ops on CPU).  No autograd, no allocations in the step,
+  so a whole training step is CUDA-graph capturable.
+
+The reference contributes no model code: it calls ``transformers.GPT2LMHeadModel`` (reference
+hivetrain/training_manager.py:39-46, 380-384).  Parameter *names* follow the HF state-dict so
+deltas / averaged models remain inter-operable; linear weights are stored ``[out, in]`` (K-major for the tcgen05 GEMM),
+i.e. transposed w.r.t. HF GPT-2's Conv1D -- :func:`to_hf_state_dict` converts.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from .arena import Arena, Manifest, init_arena_
+
+
+@dataclass
+class ModelConfig:
+    family: str = "gpt2"  # gpt2 | llama
+    vocab_size: int = 50258  # GPT-2 BPE + [PAD] (reference neurons/miner.py:61-62)
+    n_positions: int = 1024
+    n_embd: int = 768
+    n_layer: int = 12
+    n_head: int = 12
+    n_kv_head: Optional[int] = None
+    ffn: Optional[int] = None
+    eps: float = 1e-5
+    rope_theta: float = 500000.0
+    name: str = "gpt2"
+
+    @property
+    def head_dim(self) -> int:
+        return self.n_embd // self.n_head
+
+    @property
+    def kv_heads(self) -> int:
+        return self.n_kv_head or self.n_head
+
+    @property
+    def ffn_dim(self) -> int:
+        return self.ffn or 4 * self.n_embd
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.n_head + 2 * self.kv_heads) * self.head_dim
+
+
+PRESETS: Dict[str, ModelConfig] = {
+    "gpt2": ModelConfig(name="gpt2"),
+    "gpt2-small": ModelConfig(name="gpt2"),
+    "gpt2-medium": ModelConfig(name="gpt2-medium", n_embd=1024, n_layer=24, n_head=16),
+    "gpt2-tiny": ModelConfig(name="gpt2-tiny", vocab_size=512, n_positions=128, n_embd=128, n_layer=2, n_head=2),
+    "llama-3.2-1b": ModelConfig(family="llama", name="llama-3.2-1b", vocab_size=128256, n_positions=131072, n_embd=2048,
+                                n_layer=16, n_head=32, n_kv_head=8, ffn=8192, eps=1e-5, rope_theta=500000.0),
+    "llama-tiny": ModelConfig(family="llama", name="llama-tiny", vocab_size=512, n_positions=256, n_embd=128, n_layer=2,
+                              n_head=4, n_kv_head=2, ffn=256, eps=1e-5, rope_theta=10000.0),
+}
+
+
+def get_config(name: str) -> ModelConfig:
+    key = name.lower().replace("openai-community/", "").replace("_", "-")
+    if key not in PRESETS:
+        raise KeyError(f"unknown model {name!r}; known: {sorted(PRESETS)}")
+    return PRESETS[key]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# manifests
+# ---------------------------------------------------------------------------------------------------------------------
+def build_manifest(cfg: ModelConfig) -> Manifest:
+    d, Fd = cfg.n_embd, cfg.ffn_dim
+    e: List[Tuple[str, Tuple[int, ...], str, bool]] = []
+    if cfg.family == "gpt2":
+        e.append(("transformer.wte.weight", (cfg.vocab_size, d), "normal", True))
+        e.append(("transformer.wpe.weight", (cfg.n_positions, d), "normal", True))
+        for l in range(cfg.n_layer):
+            p = f"transformer.h.{l}."
+            e += [
+                (p + "ln_1.weight", (d,), "ones", False), (p + "ln_1.bias", (d,), "zeros", False),
+                (p + "attn.c_attn.weight", (3 * d, d), "normal", True), (p + "attn.c_attn.bias", (3 * d,), "zeros", False),
+                (p + "attn.c_proj.weight", (d, d), "normal_resid", True), (p + "attn.c_proj.bias", (d,), "zeros", False),
+                (p + "ln_2.weight", (d,), "ones", False), (p + "ln_2.bias", (d,), "zeros", False),
+                (p + "mlp.c_fc.weight", (Fd, d), "normal", True), (p + "mlp.c_fc.bias", (Fd,), "zeros", False),
+                (p + "mlp.c_proj.weight", (d, Fd), "normal_resid", True), (p + "mlp.c_proj.bias", (d,), "zeros", False),
+            ]
+        e += [("transformer.ln_f.weight", (d,), "ones", False), ("transformer.ln_f.bias", (d,), "zeros", False)]
+    elif cfg.family == "llama":
+        hd = cfg.head_dim
+        e.append(("model.embed_tokens.weight", (cfg.vocab_size, d), "normal", True))
+        for l in range(cfg.n_layer):
+            p = f"model.layers.{l}."
+            e += [
+                (p + "input_layernorm.weight", (d,), "ones", False),
+                (p + "self_attn.q_proj.weight", (cfg.n_head * hd, d), "normal", True),
+                (p + "self_attn.k_proj.weight", (cfg.kv_heads * hd, d), "normal", True),
+                (p + "self_attn.v_proj.weight", (cfg.kv_heads * hd, d), "normal", True),
+                (p + "self_attn.o_proj.weight", (d, cfg.n_head * hd), "normal_resid", True),
+                (p + "post_attention_layernorm.weight", (d,), "ones", False),
+                (p + "mlp.gate_proj.weight", (Fd, d), "normal", True),
+                (p + "mlp.up_proj.weight", (Fd, d), "normal", True),
+                (p + "mlp.down_proj.weight", (d, Fd), "normal_resid", True),
+            ]
+        e.append(("model.norm.weight", (d,), "ones", False))
+    else:
+        raise ValueError(cfg.family)
+    return Manifest(e)
+
+
+def fused_view(man: Manifest, flat: torch.Tensor, names: List[str]) -> torch.Tensor:
+    """One [sum(rows), cols] matrix over consecutive arena tensors (q|k|v, gate|up): requires gap-free placement."""
+    specs = [man[n] for n in names]
+    cols = specs[0].shape[1]
+    off = specs[0].offset
+    rows = 0
+    for s in specs:
+        assert s.offset == off + rows * cols and s.shape[1] == cols, f"{s.name} is not contiguous with its group"
+        rows += s.shape[0]
+    return flat[off:off + rows * cols].view(rows, cols)
+
+
+class LayerParams:
+    """Per-layer views (compute dtype) or grad views (fp32) resolved once."""
+
+    def __init__(self, cfg: ModelConfig, man: Manifest, flat: torch.Tensor, l: int):
+        v = lambda n: man.view(flat, n)
+        if cfg.family == "gpt2":
+            p = f"transformer.h.{l}."
+            self.ln1_w, self.ln1_b = v(p + "ln_1.weight"), v(p + "ln_1.bias")
+            self.qkv_w, self.qkv_b = v(p + "attn.c_attn.weight"), v(p + "attn.c_attn.bias")
+            self.o_w, self.o_b = v(p + "attn.c_proj.weight"), v(p + "attn.c_proj.bias")
+            self.ln2_w, self.ln2_b = v(p + "ln_2.weight"), v(p + "ln_2.bias")
+            self.fc_w, self.fc_b = v(p + "mlp.c_fc.weight"), v(p + "mlp.c_fc.bias")
+            self.proj_w, self.proj_b = v(p + "mlp.c_proj.weight"), v(p + "mlp.c_proj.bias")
+        else:
+            p = f"model.layers.{l}."
+            self.ln1_w, self.ln1_b = v(p + "input_layernorm.weight"), None
+            self.qkv_w = fused_view(man, flat, [p + "self_attn.q_proj.weight", p + "self_attn.k_proj.weight",
+                                                p + "self_attn.v_proj.weight"])
+            self.qkv_b = None
+            self.o_w, self.o_b = v(p + "self_attn.o_proj.weight"), None
+            self.ln2_w, self.ln2_b = v(p + "post_attention_layernorm.weight"), None
+            self.fc_w = fused_view(man, flat, [p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight"])
+            self.fc_b = None
+            self.proj_w, self.proj_b = v(p + "mlp.down_proj.weight"), None
+
+
+class ModelParams:
+    def __init__(self, cfg: ModelConfig, man: Manifest, flat: torch.Tensor):
+        v = lambda n: man.view(flat, n)
+        if cfg.family == "gpt2":
+            self.wte, self.wpe = v("transformer.wte.weight"), v("transformer.wpe.weight")
+            self.lnf_w, self.lnf_b = v("transformer.ln_f.weight"), v("transformer.ln_f.bias")
+        else:
+            self.wte, self.wpe = v("model.embed_tokens.weight"), None
+            self.lnf_w, self.lnf_b = v("model.norm.weight"), None
+        self.layers = [LayerParams(cfg, man, flat, l) for l in range(cfg.n_layer)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _norm(cfg, x, w, b):
+    if cfg.family == "gpt2":
+        return F.layer_norm(x, (x.shape[-1],), w, b, cfg.eps)
+    rs = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + cfg.eps)
+    return x * rs * w
+
+
+def _rope(x, theta):  # x [B,T,h,hd]
+    B, T, h, hd = x.shape
+    half = hd // 2
+    inv = 1.0 / (theta ** (torch.arange(0, half, device=x.device, dtype=torch.float32) / half))
+    ang = torch.arange(T, device=x.device, dtype=torch.float32)[:, None] * inv[None, :]
+    c, s = ang.cos()[None, :, None, :], ang.sin()[None, :, None, :]
+    x1, x2 = x[..., :half], x[..., half:]
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1)
+
+
+def make_targets(input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """HF causal-LM shift: position t predicts labels[t+1]; the last position is ignored (-1).
+
+    The reference passes ``labels=input_ids`` with PAD *not* masked (reference neurons/miner.py:95-99,
+    hivetrain/training_manager.py:383) -- we keep that: only negative labels are ignored.
+    """
+    lab = input_ids if labels is None else labels
+    tgt = torch.full_like(lab, -1)
+    tgt[..., :-1] = lab[..., 1:]
+    return tgt
+
+
+def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_ids: torch.Tensor) -> torch.Tensor:
+    P = ModelParams(cfg, man, theta)
+    B, T = input_ids.shape
+    H, Hkv, hd = cfg.n_head, cfg.kv_heads, cfg.head_dim
+    x = P.wte[input_ids]
+    if P.wpe is not None:
+        x = x + P.wpe[:T][None]
+    mask = torch.ones(T, T, dtype=torch.bool, device=theta.device).tril()
+    for L in P.layers:
+        h = _norm(cfg, x, L.ln1_w, L.ln1_b)
+        qkv = F.linear(h, L.qkv_w, L.qkv_b)
+        q, k, v = qkv.split([H * hd, Hkv * hd, Hkv * hd], dim=-1)
+        q, k, v = q.view(B, T, H, hd), k.view(B, T, Hkv, hd), v.view(B, T, Hkv, hd)
+        if cfg.family == "llama":
+            q, k = _rope(q, cfg.rope_theta), _rope(k, cfg.rope_theta)
+        q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+        if Hkv != H:
+            k = k.repeat_interleave(H // Hkv, dim=1)
+            v = v.repeat_interleave(H // Hkv, dim=1)
+        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        s = s.masked_fill(~mask, float("-inf"))
+        a = torch.softmax(s, dim=-1) @ v
+        a = a.transpose(1, 2).reshape(B, T, H * hd)
+        x = x + F.linear(a, L.o_w, L.o_b)
+        h = _norm(cfg, x, L.ln2_w, L.ln2_b)
+        u = F.linear(h, L.fc_w, L.fc_b)
+        if cfg.family == "gpt2":
+            act = F.gelu(u, approximate="tanh")
+        else:
+            g, up = u.chunk(2, dim=-1)
+            act = F.silu(g) * up
+        x = x + F.linear(act, L.proj_w, L.proj_b)
+    x = _norm(cfg, x, P.lnf_w, P.lnf_b)
+    return F.linear(x, P.wte)
+
+
+def oracle_loss(cfg, man, theta, input_ids, labels=None) -> torch.Tensor:
+    logits = oracle_logits(cfg, man, theta, input_ids)
+    tgt = make_targets(input_ids, labels)
+    return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), tgt.view(-1).long(), ignore_index=-1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# explicit engine
+# ---------------------------------------------------------------------------------------------------------------------
+class TransformerEngine:
+    """Static-buffer forward/backward.  ``params`` is the compute-dtype arena (bf16 on GPU), ``grads`` the fp32 arena."""
+
+    def __init__(self, cfg: ModelConfig, manifest: Manifest, params: torch.Tensor, grads: Optional[torch.Tensor],
+                 batch: int, seq: int, lm_chunk: int = 8192):
+        self.cfg, self.man = cfg, manifest
+        self.B, self.T, self.M = batch, seq, batch * seq
+        assert seq <= cfg.n_positions
+        self.dev = params.device
+        self.cdtype = params.dtype
+        self.P = ModelParams(cfg, manifest, params)
+        self.G = ModelParams(cfg, manifest, grads) if grads is not None else None
+        self.grads = grads
+        d, Fd, M = cfg.n_embd, cfg.ffn_dim, self.M
+        mk = lambda *shape, dtype=None: torch.empty(*shape, dtype=dtype or self.cdtype, device=self.dev)
+        L = cfg.n_layer
+        glu = cfg.family == "llama"
+        self.xs = [mk(M, d) for _ in range(L + 1)]  # residual stream at layer boundaries
+        self.xmid = [mk(M, d) for _ in range(L)]
+        self.h1 = [mk(M, d) for _ in range(L)]
+        self.h2 = [mk(M, d) for _ in range(L)]
+        self.qkv = [mk(M, cfg.qkv_dim) for _ in range(L)]
+        self.att = [mk(M, cfg.n_head * cfg.head_dim) for _ in range(L)]
+        self.lse = [mk(batch, cfg.n_head, seq, dtype=torch.float32) for _ in range(L)]
+        self.u = [mk(M, 2 * Fd if glu else Fd) for _ in range(L)]  # pre-activation
+        self.act = [mk(M, Fd) for _ in range(L)]
+        f32 = torch.float32
+        self.mean1 = [mk(M, dtype=f32) for _ in range(L)]
+        self.rstd1 = [mk(M, dtype=f32) for _ in range(L)]
+        self.mean2 = [mk(M, dtype=f32) for _ in range(L)]
+        self.rstd2 = [mk(M, dtype=f32) for _ in range(L)]
+        self.xf = mk(M, d)
+        self.meanf, self.rstdf = mk(M, dtype=f32), mk(M, dtype=f32)
+        self.lm_chunk = min(lm_chunk, M)
+        self.ldl = (cfg.vocab_size + 63) // 64 * 64  # padded logits pitch (16 B aligned rows for TMA)
+        self.logits = mk(self.lm_chunk, self.ldl)
+        self.losses = mk(M, dtype=f32)
+        self.loss = torch.zeros((), dtype=f32, device=self.dev)
+        # backward scratch
+        self.dx = mk(M, d)
+        self.dx2 = mk(M, d)
+        self.dxf = mk(M, d)
+        self.dh = mk(M, d)
+        self.dqkv = mk(M, cfg.qkv_dim)
+        self.datt = mk(M, cfg.n_head * cfg.head_dim)
+        self.du = mk(M, 2 * Fd if glu else Fd)
+        self.dact = mk(M, Fd) if glu else None
+        self.targets = torch.full((batch, seq), -1, dtype=torch.int32, device=self.dev)
+        self.ids = torch.zeros((batch, seq), dtype=torch.int32, device=self.dev)
+
+    # -- helpers ---------------------------------------------------------------------------------------------------
+    def _norm_fwd(self, x, w, b, out, mean, rstd):
+        if self.cfg.family == "gpt2":
+            ops.layernorm_fwd(x, w, b, self.cfg.eps, out, mean, rstd)
+        else:
+            ops.rmsnorm_fwd(x, w, self.cfg.eps, out, rstd)
+
+    def _norm_bwd(self, dy, x, w, mean, rstd, dx_out, dw, db, dresid):
+        if self.cfg.family == "gpt2":
+            ops.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
+        else:
+            ops.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
+
+    def set_batch(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
+        """Copy a batch into the static id/target buffers (non-blocking when the source is pinned)."""
+        self.ids.copy_(input_ids.view(self.B, self.T), non_blocking=True)
+        tgt = self.targets
+        src = self.ids if labels is None else labels.view(self.B, self.T)
+        tgt[:, :-1].copy_(src[:, 1:], non_blocking=True)
+
+    # -- forward ---------------------------------------------------------------------------------------------------
+    def forward(self, train: bool = True) -> None:
+        cfg, P = self.cfg, self.P
+        B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
+        ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0])
+        for l, Lp in enumerate(P.layers):
+            x = self.xs[l]
+            self._norm_fwd(x, Lp.ln1_w, Lp.ln1_b, self.h1[l], self.mean1[l], self.rstd1[l])
+            ops.gemm(self.h1[l], Lp.qkv_w, self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b)
+            if cfg.family == "llama":
+                ops.rope_(self.qkv[l], B, T, H, Hkv, hd, cfg.rope_theta)
+            ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv)
+            ops.gemm(self.att[l], Lp.o_w, self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
+                     aux=x)
+            self._norm_fwd(self.xmid[l], Lp.ln2_w, Lp.ln2_b, self.h2[l], self.mean2[l], self.rstd2[l])
+            if cfg.family == "gpt2":
+                ops.gemm(self.h2[l], Lp.fc_w, self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l])
+            else:
+                ops.gemm(self.h2[l], Lp.fc_w, self.u[l])
+                ops.swiglu_fwd(self.u[l], self.act[l])
+            ops.gemm(self.act[l], Lp.proj_w, self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
+                     bias=Lp.proj_b, aux=self.xmid[l])
+        self._norm_fwd(self.xs[-1], P.lnf_w, P.lnf_b, self.xf, self.meanf, self.rstdf)
+
+    def _lm_head(self, backward: bool) -> None:
+        cfg, P = self.cfg, self.P
+        V = cfg.vocab_size
+        n_valid = self.B * (self.T - 1)
+        scale = 1.0 / max(n_valid, 1)
+        tgt = self.targets.view(-1)
+        for c0 in range(0, self.M, self.lm_chunk):
+            c1 = min(self.M, c0 + self.lm_chunk)
+            lg = self.logits[:c1 - c0]
+            ops.gemm(self.xf[c0:c1], P.wte, lg[:, :V] if not lg.is_cuda else lg, n_cols=V)
+            ops.ce_fwd_bwd(lg, tgt[c0:c1], V, self.losses[c0:c1], scale if backward else None)
+            if backward:
+                ops.gemm(lg, P.wte, self.dxf[c0:c1], b_mn=True, k_cols=V)  # dxf = dlogits @ wte
+                ops.gemm(lg, self.xf[c0:c1], self.G.wte, a_mn=True, b_mn=True, accumulate=True, m_rows=V)  # dwte += dlogits^T xf
+        torch.sum(self.losses, dim=0, out=self.loss)
+        self.loss.mul_(scale)
+
+    def forward_loss(self) -> torch.Tensor:
+        """Eval forward: mean next-token CE over the batch in the static buffers (device scalar)."""
+        self.forward(train=False)
+        self._lm_head(backward=False)
+        return self.loss
+
+    # -- backward --------------------------------------------------------------------------------------------------
+    def forward_backward(self, zero_grad: bool = True) -> torch.Tensor:
+        cfg, P, G = self.cfg, self.P, self.G
+        B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
+        if zero_grad:
+            self.grads.zero_()
+        self.forward(train=True)
+        self._lm_head(backward=True)
+        dx, dx2 = self.dx, self.dx2
+        self._norm_bwd(self.dxf, self.xs[-1], P.lnf_w, self.meanf, self.rstdf, dx, G.lnf_w, G.lnf_b, None)
+        for l in range(cfg.n_layer - 1, -1, -1):
+            Lp, Lg = P.layers[l], G.layers[l]
+            # ---- MLP block ----
+            if cfg.family == "gpt2":
+                ops.gemm(dx, Lp.proj_w, self.du, b_mn=True, epi="dgelu", aux=self.u[l])
+            else:
+                ops.gemm(dx, Lp.proj_w, self.dact, b_mn=True)
+                ops.swiglu_bwd(self.dact, self.u[l], self.du)
+            ops.gemm(dx, self.act[l], Lg.proj_w, a_mn=True, b_mn=True, accumulate=True)
+            if Lg.proj_b is not None:
+                ops.colsum(dx, Lg.proj_b)
+            ops.gemm(self.du, Lp.fc_w, self.dh, b_mn=True)
+            ops.gemm(self.du, self.h2[l], Lg.fc_w, a_mn=True, b_mn=True, accumulate=True)
+            if Lg.fc_b is not None:
+                ops.colsum(self.du, Lg.fc_b)
+            self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx)
+            dx, dx2 = dx2, dx
+            # ---- attention block ----
+            ops.gemm(dx, Lp.o_w, self.datt, b_mn=True)
+            ops.gemm(dx, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
+            if Lg.o_b is not None:
+                ops.colsum(dx, Lg.o_b)
+            ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv)
+            if cfg.family == "llama":
+                ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
+            ops.gemm(self.dqkv, Lp.qkv_w, self.dh, b_mn=True)
+            ops.gemm(self.dqkv, self.h1[l], Lg.qkv_w, a_mn=True, b_mn=True, accumulate=True)
+            if Lg.qkv_b is not None:
+                ops.colsum(self.dqkv, Lg.qkv_b)
+            self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx)
+            dx, dx2 = dx2, dx
+        ops.embed_bwd(dx, self.ids, G.wte, G.wpe)
+        return self.loss
+
+
+def to_hf_state_dict(cfg: ModelConfig, arena: Arena) -> Dict[str, torch.Tensor]:
+    """HF-compatible state dict (GPT-2 Conv1D weights transposed back to [in, out]; tied lm_head added -> 149 keys)."""
+    sd = arena.state_dict(clone=True)
+    if cfg.family == "gpt2":
+        for k in list(sd):
+            if k.endswith(("c_attn.weight", "c_proj.weight", "c_fc.weight")):
+                sd[k] = sd[k].t().contiguous()
+        sd["lm_head.weight"] = sd["transformer.wte.weight"]
+    else:
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    return sd
+
+
+def new_model(name_or_cfg, device="cpu", dtype=torch.float32, seed: int = 0) -> Tuple[ModelConfig, Manifest, Arena]:
+    cfg = get_config(name_or_cfg) if isinstance(name_or_cfg, str) else name_or_cfg
+    man = build_manifest(cfg)
+    arena = Arena(man, dtype=torch.float32, device="cpu")
+    init_arena_(arena, n_layer=cfg.n_layer, seed=seed)
+    if str(device) != "cpu" or dtype != torch.float32:
+        arena = Arena(man, flat=arena.flat.to(device=device, dtype=dtype))
+    return cfg, man, arena
