@@ -1,0 +1,444 @@
+// Bandwidth-bound transformer kernels for sm_100a: embedding fwd/bwd, LayerNorm / RMSNorm fwd+bwd, fused
+// cross-entropy (loss + dlogits in place, row resident in shared memory), column sums (bias grads), SwiGLU, RoPE.
+// All of them are single-pass, 128-bit vectorised, fp32 math on bf16 storage.
+//
+// Parity: these replace the ATen kernels behind HF GPT-2 in the reference miner/validator/averager hot loops
+// (reference hivetrain/training_manager.py:380-392).
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace dtb {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
+                                 bf16* __restrict__ out, int M, int T, int d) {
+  const int row = blockIdx.x;
+  const int id = ids[row];
+  const int pos = row % T;
+  const uint4* w = reinterpret_cast<const uint4*>(wte + size_t(id) * d);
+  const uint4* p = wpe ? reinterpret_cast<const uint4*>(wpe + size_t(pos) * d) : nullptr;
+  uint4* o = reinterpret_cast<uint4*>(out + size_t(row) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+    float a[8], b[8];
+    unpack8(__ldg(w + i), a);
+    if (p) {
+      unpack8(__ldg(p + i), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += b[k];
+    }
+    o[i] = pack8(a);
+  }
+}
+
+__global__ void embed_bwd_kernel(const bf16* __restrict__ dx, const int* __restrict__ ids, float* __restrict__ dwte,
+                                 float* __restrict__ dwpe, int M, int T, int d) {
+  const int row = blockIdx.x;
+  const int id = ids[row];
+  const int pos = row % T;
+  const uint4* g = reinterpret_cast<const uint4*>(dx + size_t(row) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+    float a[8];
+    unpack8(__ldg(g + i), a);
+    float4* te = reinterpret_cast<float4*>(dwte + size_t(id) * d + i * 8);
+    atomicAdd(te, make_float4(a[0], a[1], a[2], a[3]));
+    atomicAdd(te + 1, make_float4(a[4], a[5], a[6], a[7]));
+    if (dwpe) {
+      float4* pe = reinterpret_cast<float4*>(dwpe + size_t(pos) * d + i * 8);
+      atomicAdd(pe, make_float4(a[0], a[1], a[2], a[3]));
+      atomicAdd(pe + 1, make_float4(a[4], a[5], a[6], a[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm: one warp per row, the row (<= 8192 elements) is held in registers between the passes.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxVecPerLane = 32;  // supports d up to 32*32*8 = 8192
+
+template <bool RMS>
+__global__ void __launch_bounds__(256) norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                       const bf16* __restrict__ b, bf16* __restrict__ out,
+                                                       float* __restrict__ mean, float* __restrict__ rstd, int M, int d,
+                                                       float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nvec = d / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(warp) * d);
+  float sum = 0.f, sq = 0.f;
+  for (int i = lane; i < nvec; i += 32) {
+    float a[8];
+    unpack8(__ldg(xr + i), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sum += a[k];
+      sq += a[k] * a[k];
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  const float mu = RMS ? 0.f : sum / d;
+  const float var = RMS ? sq / d : fmaxf(sq / d - mu * mu, 0.f);
+  const float rs = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean) mean[warp] = mu;
+    rstd[warp] = rs;
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + size_t(warp) * d);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+  for (int i = lane; i < nvec; i += 32) {
+    float a[8], g[8], bb[8];
+    unpack8(__ldg(xr + i), a);  // second read hits L1/L2
+    unpack8(__ldg(wv + i), g);
+    if (!RMS && b) unpack8(__ldg(bv + i), bb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float y = (a[k] - mu) * rs * g[k];
+      if (!RMS && b) y += bb[k];
+      a[k] = y;
+    }
+    o[i] = pack8(a);
+  }
+}
+
+// Backward: dx = (g - mean(g) - xhat*mean(g*xhat)) * rstd  (+ dresid);   dw += sum_rows dy*xhat;  db += sum_rows dy.
+// Persistent warps stride over rows; per-lane column partials for dw/db live in shared memory (fp32), flushed with
+// one atomicAdd per column per block.
+template <bool RMS>
+__global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                       const bf16* __restrict__ w, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const bf16* __restrict__ dresid,
+                                                       bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                       int M, int d) {
+  extern __shared__ float sm[];  // [2][d]
+  float* s_dw = sm;
+  float* s_db = sm + d;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nvec = d / 8;
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  for (int row = blockIdx.x * warps_per_block + wib; row < M; row += gridDim.x * warps_per_block) {
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * d);
+    const float mu = RMS ? 0.f : mean[row];
+    const float rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      float a[8], g[8], ww[8];
+      unpack8(__ldg(dyr + i), g);
+      unpack8(__ldg(xr + i), a);
+      unpack8(__ldg(wv + i), ww);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (a[k] - mu) * rs;
+        const float gg = g[k] * ww[k];
+        s1 += gg;
+        s2 += gg * xh;
+        atomicAdd(&s_dw[i * 8 + k], g[k] * xh);  // shared-memory fp32 atomics, distinct addresses within a warp
+        if (!RMS) atomicAdd(&s_db[i * 8 + k], g[k]);
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    if (RMS) s1 = 0.f;
+    uint4* o = reinterpret_cast<uint4*>(dx + size_t(row) * d);
+    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
+    for (int i = lane; i < nvec; i += 32) {
+      float a[8], g[8], ww[8], r[8];
+      unpack8(__ldg(dyr + i), g);
+      unpack8(__ldg(xr + i), a);
+      unpack8(__ldg(wv + i), ww);
+      if (rr) unpack8(__ldg(rr + i), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (a[k] - mu) * rs;
+        float v = (g[k] * ww[k] - s1 - xh * s2) * rs;
+        if (rr) v += r[k];
+        a[k] = v;
+      }
+      o[i] = pack8(a);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(&dw[i], s_dw[i]);
+    if (!RMS && db) atomicAdd(&db[i], s_db[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused cross-entropy: one CTA per row; the row is pulled into shared memory once (<= ~100 KB for V = 50k bf16),
+// loss = lse - logit[target]; logits are overwritten in place with (softmax - onehot) * scale.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ targets,
+                                                         float* __restrict__ losses, int V, int ldl, float grad_scale,
+                                                         int write_grad) {
+  extern __shared__ uint4 srow[];
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  bf16* lr = logits + size_t(row) * ldl;
+  const int tgt = targets[row];
+  const int nvec = (V + 7) / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(lr);
+  float mx = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 q = src[i];
+    srow[i] = q;
+    float a[8];
+    unpack8(q, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (i * 8 + k < V) mx = fmaxf(mx, a[k]);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -CUDART_INF_F;
+    v = warp_max(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  mx = red[0];
+  __syncthreads();
+  float se = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float a[8];
+    unpack8(srow[i], a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (i * 8 + k < V) se += __expf(a[k] - mx);
+  }
+  se = warp_sum(se);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  se = red[0];
+  const float lse = mx + __logf(se);
+  const bool valid = tgt >= 0;
+  if (threadIdx.x == 0) {
+    float lt = valid ? __bfloat162float(reinterpret_cast<const bf16*>(srow)[tgt]) : 0.f;
+    losses[row] = valid ? (lse - lt) : 0.f;
+  }
+  if (!write_grad) return;
+  const float sc = valid ? grad_scale : 0.f;
+  const float inv = 1.f / se;
+  uint4* dst = reinterpret_cast<uint4*>(lr);
+  const int nvec_pad = ldl / 8;
+  for (int i = threadIdx.x; i < nvec_pad; i += blockDim.x) {
+    float a[8];
+    if (i < nvec) {
+      unpack8(srow[i], a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = i * 8 + k;
+        float p = (c < V) ? __expf(a[k] - mx) * inv : 0.f;
+        if (c == tgt) p -= 1.f;
+        a[k] = p * sc;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    }
+    dst[i] = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// column sum: out[N] += sum_m x[m, :]  (bias gradients).  Block = 256 threads = 32 column-vectors x 8 row lanes.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int N, int ldx,
+                                                     int rows_per_block) {
+  __shared__ float part[8][32 * 8 + 1];
+  const int cv = threadIdx.x & 31;   // column vector within the tile (8 columns each)
+  const int rl = threadIdx.x >> 5;   // row lane 0..7
+  const int col0 = blockIdx.x * 256 + cv * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col0 < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float a[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + size_t(r) * ldx + col0)), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += a[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[rl][cv * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += part[r][c];
+    atomicAdd(&out[blockIdx.x * 256 + c], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SwiGLU and RoPE (Llama family)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, int M, int F) {
+  const size_t nvec = size_t(M) * F / 8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nvec; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t row = i / (F / 8), cv = i % (F / 8);
+    float g[8], u[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gu + row * 2 * F) + cv), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gu + row * 2 * F + F) + cv), u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
+    reinterpret_cast<uint4*>(out + row * F)[cv] = pack8(g);
+  }
+}
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ gu, bf16* __restrict__ dgu, int M,
+                                  int F) {
+  const size_t nvec = size_t(M) * F / 8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nvec; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t row = i / (F / 8), cv = i % (F / 8);
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gu + row * 2 * F) + cv), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gu + row * 2 * F + F) + cv), u);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + row * F) + cv), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sg = 1.f / (1.f + __expf(-g[k]));
+      dg[k] = d[k] * u[k] * sg * (1.f + g[k] * (1.f - sg));
+      du[k] = d[k] * g[k] * sg;
+    }
+    reinterpret_cast<uint4*>(dgu + row * 2 * F)[cv] = pack8(dg);
+    reinterpret_cast<uint4*>(dgu + row * 2 * F + F)[cv] = pack8(du);
+  }
+}
+// rotate-half RoPE applied in place to the q and k heads of packed qkv [M, (H+2Hkv)*hd]; one thread per (row, head, pair).
+__global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot, int row_stride, int hd, float log2_theta,
+                            float sign) {
+  const int half = hd / 2;
+  const size_t total = size_t(M) * nheads_rot * half;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int p = i % half;
+    const int h = (i / half) % nheads_rot;
+    const size_t row = i / (size_t(half) * nheads_rot);
+    const int t = row % T;
+    const float inv = exp2f(-log2_theta * float(p) / float(half));
+    float s, c;
+    sincosf(float(t) * inv, &s, &c);
+    s *= sign;
+    bf16* base = qkv + row * row_stride + size_t(h) * hd;
+    const float x1 = __bfloat162float(base[p]), x2 = __bfloat162float(base[p + half]);
+    base[p] = __float2bfloat16(x1 * c - x2 * s);
+    base[p + half] = __float2bfloat16(x2 * c + x1 * s);
+  }
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+#define KCHECK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
+
+extern "C" int dtb_embed_fwd(const int* ids, const void* wte, const void* wpe, void* out, int M, int T, int d, cudaStream_t s) {
+  embed_fwd_kernel<<<M, 128, 0, s>>>(ids, (const bf16*)wte, (const bf16*)wpe, (bf16*)out, M, T, d);
+  return KCHECK();
+}
+extern "C" int dtb_embed_bwd(const void* dx, const int* ids, float* dwte, float* dwpe, int M, int T, int d, cudaStream_t s) {
+  embed_bwd_kernel<<<M, 128, 0, s>>>((const bf16*)dx, ids, dwte, dwpe, M, T, d);
+  return KCHECK();
+}
+extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* out, float* mean, float* rstd, int M, int d,
+                            float eps, int rms, cudaStream_t s) {
+  const int warps_per_block = 8;
+  const int grid = (M + warps_per_block - 1) / warps_per_block;
+  if (rms) norm_fwd_kernel<true><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, nullptr, (bf16*)out, nullptr, rstd, M, d, eps);
+  else norm_fwd_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)out, mean, rstd, M, d, eps);
+  return KCHECK();
+}
+extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                            const void* dresid, void* dx, float* dw, float* db, int M, int d, int rms, int num_sms,
+                            cudaStream_t s) {
+  const int grid = min((M + 7) / 8, num_sms * 2);
+  const size_t smem = size_t(2) * d * sizeof(float);
+  if (rms) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    norm_bwd_kernel<true><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, nullptr, rstd,
+                                                  (const bf16*)dresid, (bf16*)dx, dw, nullptr, M, d);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    norm_bwd_kernel<false><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
+                                                   (const bf16*)dresid, (bf16*)dx, dw, db, M, d);
+  }
+  return KCHECK();
+}
+extern "C" int dtb_ce_fwd_bwd(void* logits, const int* targets, float* losses, int M, int V, int ldl, float grad_scale,
+                              int write_grad, cudaStream_t s) {
+  const size_t smem = size_t((V + 7) / 8) * 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(ce_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return 2;
+    configured = smem;
+  }
+  ce_fwd_bwd_kernel<<<M, 512, smem, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
+  return KCHECK();
+}
+extern "C" int dtb_colsum(const void* x, float* out, int M, int N, int ldx, cudaStream_t s) {
+  const int rows_per_block = 256;
+  dim3 grid((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<grid, 256, 0, s>>>((const bf16*)x, out, M, N, ldx, rows_per_block);
+  return KCHECK();
+}
+extern "C" int dtb_swiglu_fwd(const void* gu, void* out, int M, int F, int num_sms, cudaStream_t s) {
+  swiglu_fwd_kernel<<<num_sms * 8, 256, 0, s>>>((const bf16*)gu, (bf16*)out, M, F);
+  return KCHECK();
+}
+extern "C" int dtb_swiglu_bwd(const void* dout, const void* gu, void* dgu, int M, int F, int num_sms, cudaStream_t s) {
+  swiglu_bwd_kernel<<<num_sms * 8, 256, 0, s>>>((const bf16*)dout, (const bf16*)gu, (bf16*)dgu, M, F);
+  return KCHECK();
+}
+extern "C" int dtb_rope(void* qkv, int M, int T, int nheads_rot, int row_stride, int hd, float theta, int inverse, int num_sms,
+                        cudaStream_t s) {
+  rope_kernel<<<num_sms * 8, 256, 0, s>>>((bf16*)qkv, M, T, nheads_rot, row_stride, hd, log2f(theta), inverse ? -1.f : 1.f);
+  return KCHECK();
+}

@@ -1,0 +1,538 @@
+// Flat-arena kernels of the local-SGD algorithm (sm_100a):
+//   * fused multi-tensor AdamW over the whole parameter arena (+ bf16 compute copy, + optional fused delta emit)
+//   * delta emit  d = theta - theta_base   (fp32 / bf16 / block-scaled fp8 e4m3, 32-element blocks, fp32 scales)
+//   * fused kernel (a): gather -> learned weighted sum -> base add, in ONE pass:
+//         theta_new[e] = s_j * theta_base[e] + sum_i w[i,j] * delta_i[e],   s_j = sum_i w[i,j]
+//     delta_i pointers may be PEER (NVLink-mapped) addresses: the kernel issues the P2P loads itself, optionally
+//     waits on per-miner publish flags (ld.acquire.sys) and pushes the result to several destinations (peer stores),
+//     which turns it into reduce-scatter + all-gather when every rank runs it on its shard.
+//   * segmented multi-dot: G[i,j] = <g_j, theta_base_j + delta_ij - theta_avg_j>  (meta-gradient of the learned mixer)
+//   * cross-GPU flag publish / device-side barrier
+//
+// Parity: reference hivetrain/training_manager.py:391,417-421 (AdamW, delta emit), hivetrain/averaging_logic.py:
+// 422-448 (weighted average), :513-528 (meta-gradient), :121-127 (NaN screen); SURVEY.md K10, K13, K19-K24.
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+#include "sm100_ptx.cuh"
+
+namespace dtb {
+
+using bf16 = __nv_bfloat16;
+constexpr int kMaxMiners = 64;
+constexpr int kMaxOut = 16;
+
+// ------------------------------------------------------------------------------------------------------------------
+// AdamW
+// ------------------------------------------------------------------------------------------------------------------
+// hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, bias_corr1, bias_corr2
+__global__ void adam_prep_kernel(int* step, float* hyper) {
+  const int t = *step + 1;
+  *step = t;
+  hyper[6] = 1.f - powf(hyper[1], float(t));
+  hyper[7] = 1.f - powf(hyper[2], float(t));
+}
+
+template <int DELTA_MODE>  // 0: none, 1: fp32 delta, 2: bf16 delta
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, bf16* __restrict__ p16,
+                                                    const float* __restrict__ grad, float* __restrict__ m,
+                                                    float* __restrict__ v, const float* __restrict__ hyper,
+                                                    const float* __restrict__ base, void* __restrict__ delta, size_t n4) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
+  const float step_size = lr * sqrtf(hyper[7]) / hyper[6];
+  const float decay = 1.f - lr * wd;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 p = reinterpret_cast<float4*>(master)[i];
+    float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* pp = &p.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gp[k] * gs;
+      mp[k] = b1 * mp[k] + (1.f - b1) * gk;
+      vp[k] = b2 * vp[k] + (1.f - b2) * gk * gk;
+      pp[k] = (pp[k] - step_size * mp[k] / (sqrtf(vp[k]) + eps)) * decay;
+    }
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(master)[i] = p;
+    if (p16) {
+      uint2 o;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(p16)[i] = o;
+    }
+    if (DELTA_MODE != 0) {
+      const float4 b = reinterpret_cast<const float4*>(base)[i];
+      const float4 d = make_float4(p.x - b.x, p.y - b.y, p.z - b.z, p.w - b.w);
+      if (DELTA_MODE == 1) {
+        reinterpret_cast<float4*>(delta)[i] = d;
+      } else {
+        uint2 o;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(delta)[i] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// delta emit / casts
+// ------------------------------------------------------------------------------------------------------------------
+// mode 0: fp32, 1: bf16, 2: fp8 e4m3 with one fp32 scale per 32 elements (scale = amax/448; q = x/scale)
+__global__ void __launch_bounds__(256) delta_emit_kernel(const float* __restrict__ master, const float* __restrict__ base,
+                                                         void* __restrict__ out, float* __restrict__ scales, size_t n,
+                                                         int mode) {
+  // each thread handles 8 consecutive elements; 4 threads cooperate on one 32-element fp8 block
+  const size_t n8 = n / 8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 a0 = reinterpret_cast<const float4*>(master)[2 * i], a1 = reinterpret_cast<const float4*>(master)[2 * i + 1];
+    const float4 b0 = reinterpret_cast<const float4*>(base)[2 * i], b1 = reinterpret_cast<const float4*>(base)[2 * i + 1];
+    float d[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w, a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+    if (mode == 0) {
+      reinterpret_cast<float4*>(out)[2 * i] = make_float4(d[0], d[1], d[2], d[3]);
+      reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(d[4], d[5], d[6], d[7]);
+    } else if (mode == 1) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(d[2 * k], d[2 * k + 1]);
+      reinterpret_cast<uint4*>(out)[i] = o;
+    } else {
+      float amax = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(d[k]));
+      // the 4 threads of a block are lanes 4q..4q+3 (i is contiguous across lanes, n8 % 4 == 0 by arena alignment)
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+      const float scale = amax > 0.f ? amax * (1.f / 448.f) : 1.f;
+      const float inv = 1.f / scale;
+      uint2 o;
+      uint8_t* q = reinterpret_cast<uint8_t*>(&o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] = __nv_cvt_float_to_fp8(d[k] * inv, __NV_SATFINITE, __NV_E4M3);
+      reinterpret_cast<uint2*>(out)[i] = o;
+      if ((i & 3) == 0) scales[i >> 2] = scale;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 p = reinterpret_cast<const float4*>(src)[i];
+    uint2 o;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// Round reset after a base pull: master = base, p16 = bf16(base), m = v = 0 (the reference re-creates AdamW after
+// every pull: hivetrain/training_manager.py:371-377).  One pass.
+__global__ void __launch_bounds__(256) round_reset_kernel(const float* __restrict__ base, float* __restrict__ master,
+                                                          bf16* __restrict__ p16, float* __restrict__ m,
+                                                          float* __restrict__ v, size_t n4, int reset_moments) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 p = reinterpret_cast<const float4*>(base)[i];
+    reinterpret_cast<float4*>(master)[i] = p;
+    if (p16) {
+      uint2 o;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(p16)[i] = o;
+    }
+    if (reset_moments) {
+      reinterpret_cast<float4*>(m)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(v)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused kernel (a): gather -> weighted sum -> base add (-> multi-destination store)
+// ------------------------------------------------------------------------------------------------------------------
+struct AvgParams {
+  const void* delta[kMaxMiners];       // per-miner delta window (local or peer-mapped)
+  const float* dscale[kMaxMiners];     // per-miner fp8 block scales (mode 2)
+  float* out_f32[kMaxOut];             // destinations (local and/or peer) for the fp32 result
+  bf16* out_bf16[kMaxOut];             // optional bf16 compute copies
+  const uint32_t* wait_flag[kMaxMiners];  // optional: spin until *wait_flag[i] >= wait_value before touching delta[i]
+  const float* base;
+  const float* w;                      // [N, P] row-major mixing weights
+  const int64_t* chunk_start;
+  const int32_t* chunk_len;
+  const int32_t* chunk_tid;
+  int* nan_flags;                      // [N], set to 1 if miner i's delta holds a non-finite value
+  int* error_flag;                     // set to 1 on a flag-wait timeout
+  int N, P, n_out, mode;               // mode: 0 fp32, 1 bf16, 2 fp8-block
+  int chunk_begin, chunk_end;          // shard of the chunk table processed by this launch
+  uint32_t wait_value;
+};
+
+template <int MODE>
+__device__ __forceinline__ void load_delta8(const AvgParams& p, int i, size_t e, float* d) {
+  if (MODE == 0) {
+    const uint4 q0 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e);
+    const uint4 q1 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e + 4);
+    d[0] = __uint_as_float(q0.x); d[1] = __uint_as_float(q0.y); d[2] = __uint_as_float(q0.z); d[3] = __uint_as_float(q0.w);
+    d[4] = __uint_as_float(q1.x); d[5] = __uint_as_float(q1.y); d[6] = __uint_as_float(q1.z); d[7] = __uint_as_float(q1.w);
+  } else if (MODE == 1) {
+    const uint4 q = ld_relaxed_sys_v4(reinterpret_cast<const bf16*>(p.delta[i]) + e);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = __bfloat1622float2(h[k]);
+      d[2 * k] = t.x;
+      d[2 * k + 1] = t.y;
+    }
+  } else {
+    uint2 q;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(q.x), "=r"(q.y)
+                 : "l"(reinterpret_cast<const uint8_t*>(p.delta[i]) + e)
+                 : "memory");
+    float sc;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc) : "l"(p.dscale[i] + (e >> 5)) : "memory");
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(&q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __half_raw hr = __nv_cvt_fp8_to_halfraw(b[k], __NV_E4M3);
+      d[k] = __half2float(*reinterpret_cast<const __half*>(&hr)) * sc;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__ AvgParams p) {
+  __shared__ float s_w[kMaxMiners + 1];
+  // --- wait for the producers' publish flags (fused "barrier-by-flag" instead of the reference's SHA polling) ---
+  if (p.wait_value != 0) {
+    if (threadIdx.x < p.N && p.wait_flag[threadIdx.x] != nullptr) {
+      long long spins = 0;
+      while (ld_acquire_sys(p.wait_flag[threadIdx.x]) < p.wait_value) {
+        if (++spins > (1ll << 26)) {
+          *p.error_flag = 1;
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  int bad = 0;  // bitmask (per thread) of miners with non-finite data; N <= 64 -> two 32-bit words
+  int bad_hi = 0;
+  for (int c = p.chunk_begin + blockIdx.x; c < p.chunk_end; c += gridDim.x) {
+    const int j = p.chunk_tid[c];
+    const size_t start = size_t(p.chunk_start[c]);
+    const int len = p.chunk_len[c];
+    __syncthreads();
+    if (threadIdx.x < p.N) s_w[threadIdx.x] = p.w[size_t(threadIdx.x) * p.P + j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < p.N; ++i) s += s_w[i];
+      s_w[kMaxMiners] = s;
+    }
+    __syncthreads();
+    const float s_sum = s_w[kMaxMiners];
+    for (int v8 = threadIdx.x; v8 * 8 < len; v8 += blockDim.x) {
+      const size_t e = start + size_t(v8) * 8;
+      const float4 b0 = reinterpret_cast<const float4*>(p.base + e)[0];
+      const float4 b1 = reinterpret_cast<const float4*>(p.base + e)[1];
+      float acc[8] = {b0.x * s_sum, b0.y * s_sum, b0.z * s_sum, b0.w * s_sum, b1.x * s_sum, b1.y * s_sum, b1.z * s_sum, b1.w * s_sum};
+      int i = 0;
+      for (; i + 4 <= p.N; i += 4) {  // 4 miners' loads in flight per thread before the FMAs
+        float d0[8], d1[8], d2[8], d3[8];
+        load_delta8<MODE>(p, i, e, d0);
+        load_delta8<MODE>(p, i + 1, e, d1);
+        load_delta8<MODE>(p, i + 2, e, d2);
+        load_delta8<MODE>(p, i + 3, e, d3);
+        const float w0 = s_w[i], w1 = s_w[i + 1], w2 = s_w[i + 2], w3 = s_w[i + 3];
+        float chk0 = 0.f, chk1 = 0.f, chk2 = 0.f, chk3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k] += w0 * d0[k] + w1 * d1[k] + w2 * d2[k] + w3 * d3[k];
+          chk0 += d0[k] * 0.f; chk1 += d1[k] * 0.f; chk2 += d2[k] * 0.f; chk3 += d3[k] * 0.f;  // NaN/Inf -> NaN
+        }
+        if (chk0 != 0.f) { if (i < 32) bad |= 1 << i; else bad_hi |= 1 << (i - 32); }
+        if (chk1 != 0.f) { if (i + 1 < 32) bad |= 1 << (i + 1); else bad_hi |= 1 << (i + 1 - 32); }
+        if (chk2 != 0.f) { if (i + 2 < 32) bad |= 1 << (i + 2); else bad_hi |= 1 << (i + 2 - 32); }
+        if (chk3 != 0.f) { if (i + 3 < 32) bad |= 1 << (i + 3); else bad_hi |= 1 << (i + 3 - 32); }
+      }
+      for (; i < p.N; ++i) {
+        float d0[8];
+        load_delta8<MODE>(p, i, e, d0);
+        const float w0 = s_w[i];
+        float chk0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k] += w0 * d0[k];
+          chk0 += d0[k] * 0.f;
+        }
+        if (chk0 != 0.f) { if (i < 32) bad |= 1 << i; else bad_hi |= 1 << (i - 32); }
+      }
+      const float4 o0 = make_float4(acc[0], acc[1], acc[2], acc[3]), o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      uint4 ob;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+      for (int o = 0; o < p.n_out; ++o) {
+        if (p.out_f32[o]) {
+          reinterpret_cast<float4*>(p.out_f32[o] + e)[0] = o0;
+          reinterpret_cast<float4*>(p.out_f32[o] + e)[1] = o1;
+        }
+        if (p.out_bf16[o]) *reinterpret_cast<uint4*>(p.out_bf16[o] + e) = ob;
+      }
+    }
+  }
+  if (p.nan_flags) {
+    if (bad) for (int i = 0; i < 32 && i < p.N; ++i) if (bad & (1 << i)) p.nan_flags[i] = 1;
+    if (bad_hi) for (int i = 32; i < p.N; ++i) if (bad_hi & (1 << (i - 32))) p.nan_flags[i] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// segmented multi-dot (meta-gradient).  Stage 1: per chunk partial sums [num_chunks, N+1]; stage 2: per tensor reduce.
+// ------------------------------------------------------------------------------------------------------------------
+struct DotParams {
+  const void* delta[kMaxMiners];
+  const float* dscale[kMaxMiners];
+  const float* g;
+  const float* base;
+  const float* avg;
+  const int64_t* chunk_start;
+  const int32_t* chunk_len;
+  float* partial;  // [num_chunks, N+1]
+  int N, num_chunks, mode;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) multi_dot_stage1(const __grid_constant__ DotParams p) {
+  __shared__ float red[8][kMaxMiners + 1];
+  AvgParams* dummy = nullptr;
+  (void)dummy;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int c = blockIdx.x; c < p.num_chunks; c += gridDim.x) {
+    const size_t start = size_t(p.chunk_start[c]);
+    const int len = p.chunk_len[c];
+    float common = 0.f;
+    float acc[kMaxMiners];
+#pragma unroll 1
+    for (int i = 0; i < p.N; ++i) acc[i] = 0.f;
+    for (int v8 = threadIdx.x; v8 * 8 < len; v8 += blockDim.x) {
+      const size_t e = start + size_t(v8) * 8;
+      float g[8], b[8], a[8];
+      *reinterpret_cast<float4*>(g) = reinterpret_cast<const float4*>(p.g + e)[0];
+      *reinterpret_cast<float4*>(g + 4) = reinterpret_cast<const float4*>(p.g + e)[1];
+      *reinterpret_cast<float4*>(b) = reinterpret_cast<const float4*>(p.base + e)[0];
+      *reinterpret_cast<float4*>(b + 4) = reinterpret_cast<const float4*>(p.base + e)[1];
+      *reinterpret_cast<float4*>(a) = reinterpret_cast<const float4*>(p.avg + e)[0];
+      *reinterpret_cast<float4*>(a + 4) = reinterpret_cast<const float4*>(p.avg + e)[1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) common += g[k] * (b[k] - a[k]);
+#pragma unroll 1
+      for (int i = 0; i < p.N; ++i) {
+        float d[8];
+        // reuse the averaging kernel's typed loader through a layout-compatible view of the pointer tables
+        if (MODE == 0) {
+          const uint4 q0 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e);
+          const uint4 q1 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e + 4);
+          d[0] = __uint_as_float(q0.x); d[1] = __uint_as_float(q0.y); d[2] = __uint_as_float(q0.z); d[3] = __uint_as_float(q0.w);
+          d[4] = __uint_as_float(q1.x); d[5] = __uint_as_float(q1.y); d[6] = __uint_as_float(q1.z); d[7] = __uint_as_float(q1.w);
+        } else if (MODE == 1) {
+          const uint4 q = ld_relaxed_sys_v4(reinterpret_cast<const bf16*>(p.delta[i]) + e);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = __bfloat1622float2(h[k]);
+            d[2 * k] = t.x;
+            d[2 * k + 1] = t.y;
+          }
+        } else {
+          uint2 q;
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y)
+                       : "l"(reinterpret_cast<const uint8_t*>(p.delta[i]) + e) : "memory");
+          float sc;
+          asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc) : "l"(p.dscale[i] + (e >> 5)) : "memory");
+          const uint8_t* bb = reinterpret_cast<const uint8_t*>(&q);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __half_raw hr = __nv_cvt_fp8_to_halfraw(bb[k], __NV_E4M3);
+            d[k] = __half2float(*reinterpret_cast<const __half*>(&hr)) * sc;
+          }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += g[k] * d[k];
+        acc[i] += s;
+      }
+    }
+    // block reduce N+1 values
+    for (int i = 0; i <= p.N; ++i) {
+      float vsum = (i == p.N) ? common : acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+      if (lane == 0) red[wib][i] = vsum;
+    }
+    __syncthreads();
+    if (threadIdx.x <= p.N) {
+      float s = 0.f;
+      for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+      p.partial[size_t(c) * (p.N + 1) + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// one block per tensor j: out[i, j] = sum_chunks partial[c, i] + sum_chunks partial[c, N]
+__global__ void __launch_bounds__(256) multi_dot_stage2(const float* __restrict__ partial, const int32_t* __restrict__ first_chunk,
+                                                        float* __restrict__ out, int N, int P) {
+  __shared__ float red[8][kMaxMiners + 1];
+  const int j = blockIdx.x;
+  const int c0 = first_chunk[j], c1 = first_chunk[j + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int i = 0; i <= N; ++i) {
+    float s = 0.f;
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) s += partial[size_t(c) * (N + 1) + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[wib][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float s = 0.f, cm = 0.f;
+    for (int wv = 0; wv < 8; ++wv) {
+      s += red[wv][threadIdx.x];
+      cm += red[wv][N];
+    }
+    out[size_t(threadIdx.x) * P + j] = s + cm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// cross-GPU flags
+// ------------------------------------------------------------------------------------------------------------------
+struct FlagParams {
+  uint32_t* dst[kMaxMiners];  // one flag word per destination rank (peer-mapped)
+  int n;
+  uint32_t value;
+};
+// Publish: make all prior writes of this GPU visible system-wide, then release-store the round number to every peer.
+__global__ void publish_flag_kernel(const __grid_constant__ FlagParams p) {
+  __threadfence_system();
+  if (threadIdx.x < p.n && p.dst[threadIdx.x]) st_release_sys(p.dst[threadIdx.x], p.value);
+}
+// Wait until all of flags[0..n) >= value (local polling).
+__global__ void wait_flags_kernel(const uint32_t* flags, int n, int stride, uint32_t value, int* error_flag) {
+  if (threadIdx.x < n) {
+    long long spins = 0;
+    while (ld_acquire_sys(flags + size_t(threadIdx.x) * stride) < value) {
+      if (++spins > (1ll << 26)) {
+        *error_flag = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+#define KCHECK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
+
+extern "C" int dtb_adam_prep(int* step, float* hyper, cudaStream_t s) {
+  adam_prep_kernel<<<1, 1, 0, s>>>(step, hyper);
+  return KCHECK();
+}
+extern "C" int dtb_adamw(float* master, void* p16, const float* grad, float* m, float* v, const float* hyper, const float* base,
+                         void* delta, int delta_mode, size_t n, int num_sms, cudaStream_t s) {
+  const size_t n4 = n / 4;
+  const int grid = num_sms * 8;
+  if (delta_mode == 1) adamw_kernel<1><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4);
+  else if (delta_mode == 2) adamw_kernel<2><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4);
+  else adamw_kernel<0><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, nullptr, nullptr, n4);
+  return KCHECK();
+}
+extern "C" int dtb_delta_emit(const float* master, const float* base, void* out, float* scales, size_t n, int mode, int num_sms,
+                              cudaStream_t s) {
+  delta_emit_kernel<<<num_sms * 8, 256, 0, s>>>(master, base, out, scales, n, mode);
+  return KCHECK();
+}
+extern "C" int dtb_cast_f32_bf16(const float* src, void* dst, size_t n, int num_sms, cudaStream_t s) {
+  cast_f32_bf16_kernel<<<num_sms * 8, 256, 0, s>>>(src, (bf16*)dst, n / 4);
+  return KCHECK();
+}
+extern "C" int dtb_round_reset(const float* base, float* master, void* p16, float* m, float* v, size_t n, int reset_moments,
+                               int num_sms, cudaStream_t s) {
+  round_reset_kernel<<<num_sms * 8, 256, 0, s>>>(base, master, (bf16*)p16, m, v, n / 4, reset_moments);
+  return KCHECK();
+}
+
+// deltas / dscales / wait_flags: host arrays of N device pointers.  outs_f32 / outs_bf16: host arrays of n_out pointers.
+extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const uint32_t** wait_flags, uint32_t wait_value,
+                              const float* base, const float* w, const int64_t* chunk_start, const int32_t* chunk_len,
+                              const int32_t* chunk_tid, int chunk_begin, int chunk_end, float** outs_f32, void** outs_bf16,
+                              int n_out, int* nan_flags, int* error_flag, int N, int P, int mode, int grid, cudaStream_t s) {
+  if (N > kMaxMiners || n_out > kMaxOut) return 3;
+  AvgParams p{};
+  for (int i = 0; i < N; ++i) {
+    p.delta[i] = deltas[i];
+    p.dscale[i] = dscales ? dscales[i] : nullptr;
+    p.wait_flag[i] = wait_flags ? wait_flags[i] : nullptr;
+  }
+  for (int o = 0; o < n_out; ++o) {
+    p.out_f32[o] = outs_f32 ? outs_f32[o] : nullptr;
+    p.out_bf16[o] = outs_bf16 ? (bf16*)outs_bf16[o] : nullptr;
+  }
+  p.base = base; p.w = w; p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.chunk_tid = chunk_tid;
+  p.nan_flags = nan_flags; p.error_flag = error_flag; p.N = N; p.P = P; p.n_out = n_out; p.mode = mode;
+  p.chunk_begin = chunk_begin; p.chunk_end = chunk_end; p.wait_value = wait_flags ? wait_value : 0;
+  if (grid > chunk_end - chunk_begin) grid = chunk_end - chunk_begin;
+  if (grid < 1) return 0;
+  if (mode == 0) gather_avg_kernel<0><<<grid, 256, 0, s>>>(p);
+  else if (mode == 1) gather_avg_kernel<1><<<grid, 256, 0, s>>>(p);
+  else gather_avg_kernel<2><<<grid, 256, 0, s>>>(p);
+  return KCHECK();
+}
+
+extern "C" int dtb_multi_dot(const void** deltas, const float** dscales, const float* g, const float* base, const float* avg,
+                             const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* first_chunk, float* partial,
+                             float* out, int N, int P, int num_chunks, int mode, int grid, cudaStream_t s) {
+  if (N > kMaxMiners) return 3;
+  DotParams p{};
+  for (int i = 0; i < N; ++i) {
+    p.delta[i] = deltas[i];
+    p.dscale[i] = dscales ? dscales[i] : nullptr;
+  }
+  p.g = g; p.base = base; p.avg = avg; p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.partial = partial;
+  p.N = N; p.num_chunks = num_chunks; p.mode = mode;
+  if (grid > num_chunks) grid = num_chunks;
+  if (mode == 0) multi_dot_stage1<0><<<grid, 256, 0, s>>>(p);
+  else if (mode == 1) multi_dot_stage1<1><<<grid, 256, 0, s>>>(p);
+  else multi_dot_stage1<2><<<grid, 256, 0, s>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return 1;
+  multi_dot_stage2<<<P, 256, 0, s>>>(partial, first_chunk, out, N, P);
+  return KCHECK();
+}
+
+extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStream_t s) {
+  if (n > kMaxMiners) return 3;
+  FlagParams p{};
+  for (int i = 0; i < n; ++i) p.dst[i] = dsts[i];
+  p.n = n; p.value = value;
+  publish_flag_kernel<<<1, 64, 0, s>>>(p);
+  return KCHECK();
+}
+extern "C" int dtb_wait_flags(const uint32_t* flags, int n, int stride, uint32_t value, int* error_flag, cudaStream_t s) {
+  wait_flags_kernel<<<1, 64, 0, s>>>(flags, n, stride, value, error_flag);
+  return KCHECK();
+}

@@ -1,0 +1,121 @@
+"""Per-rank training state: flat arenas (fp32 master, bf16 compute copy, fp32 grads, Adam m/v, base snapshot) + the
+engine + the fused optimizer, with the whole step captured in ONE CUDA graph on a B200.
+
+This is the miner's inner loop of the reference (reference hivetrain/training_manager.py:380-392: forward, backward,
+``optimizer.step()``, ``zero_grad()``, ``loss.item()`` sync every step) re-designed for the hardware: no per-step host
+sync (the loss stays on the device), no per-tensor Python loops, launch overhead removed by graph replay.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops
+from .arena import Arena, Manifest
+from .transformer import ModelConfig, TransformerEngine, build_manifest, get_config, new_model
+
+
+class Trainer:
+    def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
+                 betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
+                 lm_chunk: int = 8192, init_flat: Optional[torch.Tensor] = None):
+        self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
+        self.man: Manifest = build_manifest(self.cfg)
+        self.device = torch.device(device)
+        self.is_cuda = self.device.type == "cuda"
+        self.batch, self.seq = batch, seq
+        n = self.man.total
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if init_flat is None:
+            _, _, a = new_model(self.cfg, seed=seed)
+            init_flat = a.flat
+        self.master = init_flat.to(**f32).clone()
+        self.base = self.master.clone()  # theta_base: the last pulled averaged model
+        self.grad = torch.zeros(n, **f32)
+        self.m = torch.zeros(n, **f32)
+        self.v = torch.zeros(n, **f32)
+        if self.is_cuda:
+            self.p16 = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            ops.cast_copy(self.master, self.p16)
+        else:
+            self.p16 = self.master  # CPU: compute directly on the fp32 master
+        self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
+        self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk)
+        self.use_graph = self.is_cuda if use_graph is None else (use_graph and self.is_cuda)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._eval_graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self.steps_done = 0
+        self.tokens_per_step = batch * seq
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _step_body(self) -> torch.Tensor:
+        loss = self.engine.forward_backward()
+        ops.adamw_step(self.master, self.p16 if self.is_cuda else None, self.grad, self.m, self.v, self.opt)
+        return loss
+
+    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimizer step on a [B,T] batch (host-pinned or device).  Returns the device-resident mean loss."""
+        self.engine.set_batch(input_ids, labels)
+        if not self.use_graph:
+            c0 = ops.launch_count()
+            loss = self._step_body()
+            self.launches_per_step = ops.launch_count() - c0
+        else:
+            if self._graph is None:
+                c0 = ops.launch_count()
+                # snapshot state, run the warm-up eagerly on a side stream (required before capture), restore, capture.
+                # The warm-up mutates optimizer state; replaying the graph will redo the step on restored state.
+                snap = (self.master.clone(), self.m.clone(), self.v.clone(), self.opt.step.clone(), self.opt.host_step)
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step_body()
+                torch.cuda.current_stream().wait_stream(s)
+                self.launches_per_step = ops.launch_count() - c0
+                self.master.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.opt.step.copy_(snap[3])
+                self.opt.host_step = snap[4]
+                ops.cast_copy(self.master, self.p16)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._step_body()
+                self.opt.host_step = snap[4]
+            self._graph.replay()
+            self.opt.host_step += 1
+            loss = self.engine.loss
+        self.steps_done += 1
+        return loss
+
+    @torch.no_grad()
+    def eval_loss(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.engine.set_batch(input_ids, labels)
+        return self.engine.forward_loss()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def emit_delta(self, out: torch.Tensor, scales: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """delta = theta - theta_base into ``out`` (usually this rank's symmetric window)."""
+        return ops.delta_emit(self.master, self.base, out, scales)
+
+    def load_base(self, new_base: torch.Tensor, lr: Optional[float] = None, reset_optimizer: bool = True) -> None:
+        """Adopt a new averaged base: theta = theta_base = new_base; optimizer re-created (moments dropped) with the
+        post-pull learning rate, exactly as reference hivetrain/training_manager.py:365-378."""
+        if new_base.data_ptr() != self.base.data_ptr():
+            self.base.copy_(new_base)
+        ops.round_reset(self.base, self.master, self.p16 if self.is_cuda else None, self.m, self.v, reset_optimizer)
+        if reset_optimizer:
+            self.opt.reset()
+        if lr is not None:
+            self.opt.set_lr(lr)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {"master": self.master, "base": self.base, "m": self.m, "v": self.v, "step": self.opt.step,
+                "hyper": self.opt.hyper}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.master.copy_(sd["master"]); self.base.copy_(sd["base"]); self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
+        self.opt.step.copy_(sd["step"]); self.opt.hyper.copy_(sd["hyper"])
+        self.opt.host_step = int(sd["step"])
+        self.opt.host["lr"] = float(sd["hyper"][0])
+        if self.is_cuda:
+            ops.cast_copy(self.master, self.p16)

@@ -347,12 +347,13 @@ class TransformerEngine:
         tgt = self.targets.view(-1)
         for c0 in range(0, self.M, self.lm_chunk):
             c1 = min(self.M, c0 + self.lm_chunk)
-            lg = self.logits[:c1 - c0]
-            ops.gemm(self.xf[c0:c1], P.wte, lg[:, :V] if not lg.is_cuda else lg, n_cols=V)
+            lg = self.logits[:c1 - c0]  # [rows, ldl] padded pitch; lgv is the logical [rows, V] view (TMA clips/zero-fills)
+            lgv = lg[:, :V]
+            ops.gemm(self.xf[c0:c1], P.wte, lgv)
             ops.ce_fwd_bwd(lg, tgt[c0:c1], V, self.losses[c0:c1], scale if backward else None)
             if backward:
-                ops.gemm(lg, P.wte, self.dxf[c0:c1], b_mn=True, k_cols=V)  # dxf = dlogits @ wte
-                ops.gemm(lg, self.xf[c0:c1], self.G.wte, a_mn=True, b_mn=True, accumulate=True, m_rows=V)  # dwte += dlogits^T xf
+                ops.gemm(lgv, P.wte, self.dxf[c0:c1], b_mn=True)  # dxf = dlogits @ wte
+                ops.gemm(lgv, self.xf[c0:c1], self.G.wte, a_mn=True, b_mn=True, accumulate=True)  # dwte += dlogits^T xf
         torch.sum(self.losses, dim=0, out=self.loss)
         self.loss.mul_(scale)
 

@@ -1,0 +1,393 @@
+"""Op layer: every hot op of the framework behind one functional API.
+
+CUDA tensors are served by the hand-written sm_100a kernels in ``csrc/`` (through :mod:`._lib`); CPU tensors by the
+PyTorch reference implementations in :mod:`.reference` (same signatures, used as test oracle).  There is no silent
+fallback on a GPU box: if CUDA is available and the kernel library is missing the first call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib, reference as ref
+from ._lib import have_kernels, use_kernels
+
+EPI = {"none": 0, "bias": 1, "bias_gelu": 2, "bias_resid": 3, "dgelu": 4, "resid": 5}
+
+_counters = {"launches": 0}
+
+
+def launch_count() -> int:
+    """Number of hand-written kernel launches issued through this module (for bench.py's ``gpu_launches``)."""
+    return _counters["launches"]
+
+
+def _tick(n: int = 1) -> None:
+    _counters["launches"] += n
+
+
+def _c(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what}: kernel launch failed (code {rc})")
+
+
+def _row_major(t: torch.Tensor, what: str) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, f"{what} must be a row-major 2D view"
+    assert t.data_ptr() % 16 == 0, f"{what} must be 16-byte aligned"
+    return t.stride(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------------------
+def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
+         splits=0):
+    """out[M,N] = epi(alpha * A @ B^T) -- see :func:`reference.gemm` for the operand conventions.
+
+    CUDA: persistent tcgen05/TMEM/TMA kernel (csrc/sm100_gemm.cu).  fp32 ``out`` is always reduce-ADDED by TMA
+    (split-K capable); pass ``accumulate=False`` to have it zeroed first.
+    """
+    if not use_kernels(out):
+        return ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
+                        accumulate=accumulate)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    lda, ldb, ldc = _row_major(a, "a"), _row_major(b, "b"), _row_major(out, "out")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, f"reduction dims differ: {K} vs {Kb}"
+    assert out.shape[0] == M and out.shape[1] == N, f"out {tuple(out.shape)} != ({M},{N})"
+    out_f32 = out.dtype == torch.float32
+    if out_f32:
+        assert epi == "none"
+        if not accumulate:
+            out.zero_()
+        if splits <= 0:
+            tiles = ((M + 127) // 128) * ((N + 255) // 256)
+            nkb = (K + 63) // 64
+            splits = max(1, min(nkb // 4 if nkb >= 8 else 1, (2 * _lib.num_sms()) // max(tiles, 1)))
+    else:
+        assert out.dtype == torch.bfloat16 and not accumulate
+        splits = 1
+    ldaux = _row_major(aux, "aux") if aux is not None else 0
+    ldc2 = _row_major(out2, "out2") if out2 is not None else 0
+    rc = _lib.lib().dtb_gemm_bf16(
+        _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), int(out_f32), EPI[epi],
+        _lib.ptr(bias), _lib.ptr(aux), ldaux, _lib.ptr(out2), ldc2, ctypes.c_float(alpha), splits, _lib.num_sms(),
+        _lib.stream_ptr())
+    _c(rc, "gemm")
+    _tick()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# embedding / norms / activations / loss
+# ---------------------------------------------------------------------------------------------------------------------
+def embed_fwd(ids, wte, wpe, out):
+    if not use_kernels(out):
+        return ref.embed_fwd(ids.long(), wte, wpe, out)
+    M, d = out.shape
+    _c(_lib.lib().dtb_embed_fwd(_lib.ptr(ids), _lib.ptr(wte), _lib.ptr(wpe), _lib.ptr(out), M, ids.shape[-1], d,
+                                _lib.stream_ptr()), "embed_fwd")
+    _tick()
+    return out
+
+
+def embed_bwd(dx, ids, dwte, dwpe):
+    if not use_kernels(dx):
+        return ref.embed_bwd(dx, ids.long(), dwte, dwpe)
+    M, d = dx.shape
+    _c(_lib.lib().dtb_embed_bwd(_lib.ptr(dx), _lib.ptr(ids), _lib.ptr(dwte), _lib.ptr(dwpe), M, ids.shape[-1], d,
+                                _lib.stream_ptr()), "embed_bwd")
+    _tick()
+
+
+def layernorm_fwd(x, w, b, eps, out, mean, rstd):
+    if not use_kernels(out):
+        return ref.layernorm_fwd(x, w, b, eps, out, mean, rstd)
+    M, d = x.shape
+    _c(_lib.lib().dtb_norm_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), _lib.ptr(mean), _lib.ptr(rstd), M, d,
+                               ctypes.c_float(eps), 0, _lib.stream_ptr()), "layernorm_fwd")
+    _tick()
+    return out
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None):
+    if not use_kernels(dx_out):
+        return ref.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
+    M, d = x.shape
+    _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dresid),
+                               _lib.ptr(dx_out), _lib.ptr(dw), _lib.ptr(db), M, d, 0, _lib.num_sms(), _lib.stream_ptr()),
+       "layernorm_bwd")
+    _tick()
+    return dx_out
+
+
+def rmsnorm_fwd(x, w, eps, out, rstd):
+    if not use_kernels(out):
+        return ref.rmsnorm_fwd(x, w, eps, out, rstd)
+    M, d = x.shape
+    _c(_lib.lib().dtb_norm_fwd(_lib.ptr(x), _lib.ptr(w), None, _lib.ptr(out), None, _lib.ptr(rstd), M, d,
+                               ctypes.c_float(eps), 1, _lib.stream_ptr()), "rmsnorm_fwd")
+    _tick()
+    return out
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid=None):
+    if not use_kernels(dx_out):
+        return ref.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
+    M, d = x.shape
+    _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), None, _lib.ptr(rstd), _lib.ptr(dresid),
+                               _lib.ptr(dx_out), _lib.ptr(dw), None, M, d, 1, _lib.num_sms(), _lib.stream_ptr()),
+       "rmsnorm_bwd")
+    _tick()
+    return dx_out
+
+
+def swiglu_fwd(gu, out):
+    if not use_kernels(out):
+        return ref.swiglu_fwd(gu, out)
+    M, Fd = out.shape
+    _c(_lib.lib().dtb_swiglu_fwd(_lib.ptr(gu), _lib.ptr(out), M, Fd, _lib.num_sms(), _lib.stream_ptr()), "swiglu_fwd")
+    _tick()
+    return out
+
+
+def swiglu_bwd(dout, gu, dgu):
+    if not use_kernels(dgu):
+        return ref.swiglu_bwd(dout, gu, dgu)
+    M, Fd = dout.shape
+    _c(_lib.lib().dtb_swiglu_bwd(_lib.ptr(dout), _lib.ptr(gu), _lib.ptr(dgu), M, Fd, _lib.num_sms(), _lib.stream_ptr()),
+       "swiglu_bwd")
+    _tick()
+    return dgu
+
+
+def rope_(qkv, B, T, H, Hkv, hd, theta, inverse=False):
+    if not use_kernels(qkv):
+        return ref.rope_(qkv, B, T, H, Hkv, hd, theta, inverse)
+    _c(_lib.lib().dtb_rope(_lib.ptr(qkv), B * T, T, H + Hkv, qkv.shape[1], hd, ctypes.c_float(theta), int(inverse),
+                           _lib.num_sms(), _lib.stream_ptr()), "rope")
+    _tick()
+    return qkv
+
+
+def ce_fwd_bwd(logits, targets, V, losses, grad_scale):
+    if not use_kernels(logits):
+        return ref.ce_fwd_bwd(logits, targets, V, losses, grad_scale)
+    M, ldl = logits.shape[0], logits.stride(0)
+    _c(_lib.lib().dtb_ce_fwd_bwd(_lib.ptr(logits), _lib.ptr(targets), _lib.ptr(losses), M, V, ldl,
+                                 ctypes.c_float(grad_scale or 0.0), int(grad_scale is not None), _lib.stream_ptr()),
+       "ce_fwd_bwd")
+    _tick()
+    return losses
+
+
+def colsum(x, out):
+    if not use_kernels(x):
+        return ref.colsum(x, out)
+    M, N = x.shape
+    _c(_lib.lib().dtb_colsum(_lib.ptr(x), _lib.ptr(out), M, N, x.stride(0), _lib.stream_ptr()), "colsum")
+    _tick()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
+    from . import attention as _att
+    return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv)
+
+
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
+    from . import attention as _att
+    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optimizer / delta / averaging
+# ---------------------------------------------------------------------------------------------------------------------
+class AdamState:
+    """Device-resident hyper-parameters + step counter so the optimizer step is CUDA-graph replayable."""
+
+    def __init__(self, device, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, grad_scale=1.0):
+        self.device = torch.device(device)
+        self.hyper = torch.tensor([lr, beta1, beta2, eps, weight_decay, grad_scale, 1.0, 1.0], dtype=torch.float32,
+                                  device=device)
+        self.step = torch.zeros((), dtype=torch.int32, device=device)
+        self.host = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)
+        self.host_step = 0
+
+    def set_lr(self, lr: float) -> None:
+        self.host["lr"] = lr
+        self.hyper[0:1].fill_(lr)
+
+    def reset(self) -> None:
+        self.step.zero_()
+        self.host_step = 0
+
+
+def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None):
+    """One fused AdamW step over the whole arena; optionally also emits ``delta = master_new - base`` (fp32 or bf16)."""
+    state.host_step += 1
+    if not use_kernels(master):
+        h = state.host
+        ref.adamw_step(master, p16, grad, m, v, lr=h["lr"], beta1=h["beta1"], beta2=h["beta2"], eps=h["eps"],
+                       weight_decay=h["weight_decay"], step=state.host_step, grad_scale=h["grad_scale"])
+        if delta is not None:
+            ref.delta_emit(master, base, delta)
+        return master
+    L = _lib.lib()
+    _c(L.dtb_adam_prep(_lib.ptr(state.step), _lib.ptr(state.hyper), _lib.stream_ptr()), "adam_prep")
+    mode = 0 if delta is None else (1 if delta.dtype == torch.float32 else 2)
+    _c(L.dtb_adamw(_lib.ptr(master), _lib.ptr(p16), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), _lib.ptr(state.hyper),
+                   _lib.ptr(base), _lib.ptr(delta), mode, ctypes.c_size_t(master.numel()), _lib.num_sms(),
+                   _lib.stream_ptr()), "adamw")
+    _tick(2)
+    return master
+
+
+DELTA_MODES = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2, getattr(torch, "float8_e4m3fn", None): 2}
+
+
+def delta_emit(master, base, out, scales=None):
+    """out = master - base in out's dtype; fp8 (uint8/float8_e4m3fn storage) is block-scaled: ``scales`` fp32[n/32]."""
+    if not use_kernels(master):
+        if scales is not None:
+            return ref_delta_emit_fp8(master, base, out, scales)
+        return ref.delta_emit(master, base, out)
+    mode = DELTA_MODES[out.dtype]
+    _c(_lib.lib().dtb_delta_emit(_lib.ptr(master), _lib.ptr(base), _lib.ptr(out), _lib.ptr(scales),
+                                 ctypes.c_size_t(master.numel()), mode, _lib.num_sms(), _lib.stream_ptr()), "delta_emit")
+    _tick()
+    return out
+
+
+def ref_delta_emit_fp8(master, base, out, scales):
+    d = (master.float() - base.float()).view(-1, 32)
+    amax = d.abs().amax(dim=1)
+    sc = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    q = (d / sc[:, None]).clamp(-448, 448).to(torch.float8_e4m3fn)
+    out.view(torch.uint8).copy_(q.view(torch.uint8).reshape(-1))
+    scales.copy_(sc)
+    return out
+
+
+def dequant_fp8(q, scales):
+    return (q.view(torch.float8_e4m3fn).float().view(-1, 32) * scales[:, None]).reshape(-1)
+
+
+def cast_copy(src, dst):
+    if not use_kernels(src) or src.dtype != torch.float32 or dst.dtype != torch.bfloat16:
+        return ref.cast_copy(src, dst)
+    _c(_lib.lib().dtb_cast_f32_bf16(_lib.ptr(src), _lib.ptr(dst), ctypes.c_size_t(src.numel()), _lib.num_sms(),
+                                    _lib.stream_ptr()), "cast")
+    _tick()
+    return dst
+
+
+def round_reset(base, master, p16, m, v, reset_moments=True):
+    """master = base, p16 = bf16(base), (m, v) = 0 in one pass (optimizer re-creation after a base pull)."""
+    if not use_kernels(master):
+        master.copy_(base)
+        if p16 is not None and p16.data_ptr() != master.data_ptr():
+            p16.copy_(base.to(p16.dtype))
+        if reset_moments:
+            m.zero_()
+            v.zero_()
+        return master
+    _c(_lib.lib().dtb_round_reset(_lib.ptr(base), _lib.ptr(master), _lib.ptr(p16), _lib.ptr(m), _lib.ptr(v),
+                                  ctypes.c_size_t(master.numel()), int(reset_moments), _lib.num_sms(), _lib.stream_ptr()),
+       "round_reset")
+    _tick()
+    return master
+
+
+def _ptr_array(ptrs: Sequence[int], ctype=ctypes.c_void_p):
+    arr = (ctype * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def _dp(t) -> int:
+    """data pointer of a tensor, a raw int address (peer-mapped memory) or None."""
+    if t is None:
+        return 0
+    return t if isinstance(t, int) else t.data_ptr()
+
+
+def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales=None, nan_flags=None, wait_flags=None,
+                 wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None):
+    """Fused kernel (a): ``theta_new = s_j*base + sum_i w[i,j]*delta_i`` written to every destination in ``outs_*``.
+
+    ``deltas`` / ``outs_*`` entries are tensors or raw (peer-mapped) device addresses.  ``chunk_range`` restricts the
+    launch to a shard of the manifest's chunk table (reduce-scatter form).  See csrc/optim_avg.cu.
+    """
+    N, P = w.shape
+    if not isinstance(outs_f32, (list, tuple)):
+        outs_f32 = [outs_f32]
+    if outs_bf16 is not None and not isinstance(outs_bf16, (list, tuple)):
+        outs_bf16 = [outs_bf16]
+    if not use_kernels(base):
+        tid = manifest.tensor_ids(base.device)
+        dl = list(deltas)
+        if dscales is not None:
+            dl = [dequant_fp8(d, s) for d, s in zip(deltas, dscales)]
+        tmp = torch.empty_like(base, dtype=torch.float32)
+        ref.weighted_avg(base, dl, w, tid, tmp, nan_flags)
+        for o in outs_f32:
+            if o is not None:
+                o.copy_(tmp)
+        for o in outs_bf16 or []:
+            if o is not None:
+                o.copy_(tmp.to(o.dtype))
+        return outs_f32[0]
+    cs, cl, ct = manifest.seg_table(base.device)
+    c0, c1 = chunk_range if chunk_range is not None else (0, cs.numel())
+    if mode is None:
+        d0 = deltas[0]
+        mode = 2 if dscales is not None else DELTA_MODES[d0.dtype]
+    n_out = max(len(outs_f32), len(outs_bf16 or []))
+    of = [_dp(o) for o in outs_f32] + [0] * (n_out - len(outs_f32))
+    ob = [_dp(o) for o in (outs_bf16 or [])] + [0] * (n_out - len(outs_bf16 or []))
+    rc = _lib.lib().dtb_gather_avg(
+        _ptr_array([_dp(d) for d in deltas]), _ptr_array([_dp(s) for s in dscales]) if dscales is not None else None,
+        _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None, ctypes.c_uint32(wait_value),
+        _lib.ptr(base), _lib.ptr(w), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(ct), c0, c1, _ptr_array(of), _ptr_array(ob),
+        n_out, _lib.ptr(nan_flags), _lib.ptr(error_flag), N, P, mode, grid or _lib.num_sms() * 8, _lib.stream_ptr())
+    _c(rc, "gather_avg")
+    _tick()
+    return outs_f32[0]
+
+
+def multi_dot(g, deltas, base, avg, manifest, out, *, dscales=None, mode=None):
+    """out[i,j] = <g_j, base_j + delta_ij - avg_j> for all miners i and manifest tensors j (segmented, one pass)."""
+    N, P = out.shape
+    if not use_kernels(g):
+        tid = manifest.tensor_ids(g.device)
+        dl = list(deltas)
+        if dscales is not None:
+            dl = [dequant_fp8(d, s) for d, s in zip(deltas, dscales)]
+        return ref.multi_dot(g, dl, base, avg, tid, P, out)
+    cs, cl, ct = manifest.seg_table(g.device)
+    nchunks = cs.numel()
+    key = ("first_chunk", str(g.device))
+    cache = manifest._chunk_cache
+    if key not in cache:
+        first = torch.searchsorted(ct.long().contiguous(), torch.arange(P + 1, device=g.device)).to(torch.int32)
+        cache[key] = (first, first, first)
+    first = cache[key][0]
+    partial = torch.empty(nchunks * (N + 1), dtype=torch.float32, device=g.device)
+    if mode is None:
+        mode = 2 if dscales is not None else DELTA_MODES[deltas[0].dtype]
+    rc = _lib.lib().dtb_multi_dot(
+        _ptr_array([_dp(d) for d in deltas]), _ptr_array([_dp(s) for s in dscales]) if dscales is not None else None,
+        _lib.ptr(g), _lib.ptr(base), _lib.ptr(avg), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(first), _lib.ptr(partial),
+        _lib.ptr(out), N, P, nchunks, mode, _lib.num_sms() * 4, _lib.stream_ptr())
+    _c(rc, "multi_dot")
+    _tick(2)
+    return out

@@ -1,0 +1,46 @@
+"""Causal self-attention op (packed qkv layout).
+
+CUDA path: hand-written tcgen05 kernel (csrc/sm100_attention.cu) when built; the PyTorch reference otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib, reference as ref
+
+
+def _kernel_ok(qkv, T, hd) -> bool:
+    if not _lib.use_kernels(qkv):
+        return False
+    L = _lib.lib()
+    return hasattr(L, "dtb_attention_fwd") and hd == 64 and T % 64 == 0
+
+
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
+    Hkv = Hkv or H
+    if _kernel_ok(qkv, T, hd):
+        from . import _tick
+        rc = _lib.lib().dtb_attention_fwd(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(lse), B, T, H, Hkv, hd, qkv.stride(0),
+                                          out.stride(0), ctypes.c_float(1.0 / math.sqrt(hd)), _lib.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"attention_fwd kernel failed ({rc})")
+        _tick()
+        return out
+    return ref.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv)
+
+
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
+    Hkv = Hkv or H
+    if _kernel_ok(qkv, T, hd) and hasattr(_lib.lib(), "dtb_attention_bwd"):
+        from . import _tick
+        rc = _lib.lib().dtb_attention_bwd(_lib.ptr(dout), _lib.ptr(qkv), _lib.ptr(out), _lib.ptr(lse), _lib.ptr(dqkv), B, T,
+                                          H, Hkv, hd, qkv.stride(0), out.stride(0), ctypes.c_float(1.0 / math.sqrt(hd)),
+                                          _lib.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"attention_bwd kernel failed ({rc})")
+        _tick()
+        return dqkv
+    return ref.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)

@@ -1,0 +1,289 @@
+"""Delta / base exchange planes.
+
+=============  =====================================================================================================
+``peer``       one-sided symmetric windows over NVLink/NVSwitch; the averaging is ONE fused kernel that pulls peer
+               deltas, applies the learned weights, adds the base and pushes the result (csrc/optim_avg.cu).
+``collective`` ``all_gather`` + torch weighted sum + ``broadcast`` over a process group (NCCL = the reference-style
+               baseline this framework must beat; gloo = CPU plumbing).
+``disk``       files in a shared directory (the analogue of the reference's ``LocalHFManager`` /
+               ``LocalAverager`` fakes: reference hivetrain/hf_manager.py:200-241, averaging_logic.py:272-332).
+=============  =====================================================================================================
+
+All planes move *flat arenas* (see models/arena.py), never ``dict[str, Tensor]``.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..models.arena import Manifest
+
+DELTA_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp8": torch.uint8}
+
+
+class Exchange:
+    """Interface (round-based; ``round`` is a monotonically increasing integer replacing the reference's commit SHA)."""
+
+    kind = "abstract"
+    one_sided = True
+
+    def publish_delta(self, trainer, round: int) -> None:
+        raise NotImplementedError
+
+    def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
+        """fp32-decodable flat delta of miner ``src`` for ``round`` or ``None`` if it has not been published."""
+        raise NotImplementedError
+
+    def publish_base(self, base: torch.Tensor, round: int) -> None:
+        raise NotImplementedError
+
+    def base_round(self) -> int:
+        raise NotImplementedError
+
+    def fetch_base(self, out: torch.Tensor) -> int:
+        raise NotImplementedError
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# disk
+# ---------------------------------------------------------------------------------------------------------------------
+class DiskExchange(Exchange):
+    kind = "disk"
+
+    def __init__(self, root: str, rank: int, manifest: Manifest, delta_dtype: str = "fp32"):
+        self.root, self.rank, self.man = root, rank, manifest
+        self.delta_dtype = DELTA_DTYPES[delta_dtype]
+        os.makedirs(os.path.join(root, "deltas"), exist_ok=True)
+        os.makedirs(os.path.join(root, "base"), exist_ok=True)
+
+    def _delta_path(self, src: int) -> str:
+        return os.path.join(self.root, "deltas", f"weight_diff_{src}.pt")
+
+    def _base_path(self) -> str:
+        return os.path.join(self.root, "base", "averaged_model.pt")
+
+    @staticmethod
+    def _atomic_save(obj, path: str) -> None:
+        tmp = f"{path}.tmp.{os.getpid()}"
+        torch.save(obj, tmp)
+        os.replace(tmp, path)  # readers never observe a half-written file (the reference sleeps 10 s instead)
+
+    def publish_delta(self, trainer, round: int) -> None:
+        d = torch.empty(self.man.total, dtype=self.delta_dtype if self.delta_dtype != torch.uint8 else torch.float32,
+                        device=trainer.master.device)
+        trainer.emit_delta(d)
+        self._atomic_save({"round": round, "fingerprint": self.man.fingerprint(), "delta": d.cpu()}, self._delta_path(self.rank))
+
+    def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
+        p = self._delta_path(src)
+        if not os.path.exists(p):
+            return None
+        try:
+            blob = torch.load(p, map_location="cpu", weights_only=False)
+        except Exception:
+            return None
+        if blob.get("fingerprint") != self.man.fingerprint() or blob["delta"].numel() != self.man.total:
+            return None  # shape screen (reference averaging_logic.py:406-410)
+        if round >= 0 and blob.get("round", -1) < round:
+            return None
+        return blob["delta"]
+
+    def publish_base(self, base: torch.Tensor, round: int) -> None:
+        self._atomic_save({"round": round, "fingerprint": self.man.fingerprint(), "base": base.detach().float().cpu()},
+                          self._base_path())
+
+    def base_round(self) -> int:
+        p = self._base_path()
+        if not os.path.exists(p):
+            return -1
+        try:
+            return int(torch.load(p, map_location="cpu", weights_only=False)["round"])
+        except Exception:
+            return -1
+
+    def base_hash(self) -> Optional[str]:
+        p = self._base_path()
+        if not os.path.exists(p):
+            return None
+        h = hashlib.sha256()
+        with open(p, "rb") as f:
+            for chunk in iter(lambda: f.read(1 << 20), b""):
+                h.update(chunk)
+        return h.hexdigest()
+
+    def fetch_base(self, out: torch.Tensor) -> int:
+        blob = torch.load(self._base_path(), map_location="cpu", weights_only=False)
+        out.copy_(blob["base"].to(out.device))
+        return int(blob["round"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# collectives (baseline / CPU plumbing)
+# ---------------------------------------------------------------------------------------------------------------------
+class CollectiveExchange(Exchange):
+    """Synchronous rounds over a process group: all ranks call :meth:`allgather_average` together."""
+
+    kind = "collective"
+    one_sided = False
+
+    def __init__(self, manifest: Manifest, group=None, delta_dtype: str = "fp32"):
+        self.man, self.group = manifest, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.delta_dtype = DELTA_DTYPES[delta_dtype] if delta_dtype != "fp8" else torch.bfloat16
+        self._gathered: Optional[torch.Tensor] = None
+        self._round = 0
+
+    def allgather_deltas(self, trainer) -> torch.Tensor:
+        n = self.man.total
+        dev = trainer.master.device
+        mine = torch.empty(n, dtype=self.delta_dtype, device=dev)
+        trainer.emit_delta(mine)
+        if self._gathered is None or self._gathered.device != dev:
+            self._gathered = torch.empty(self.world, n, dtype=self.delta_dtype, device=dev)
+        dist.all_gather_into_tensor(self._gathered.view(-1), mine, group=self.group)
+        return self._gathered
+
+    def allgather_average(self, trainer, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """The NCCL(+ATen) baseline of fused kernel (a): all_gather, then N weighted axpys + base add."""
+        g = self.allgather_deltas(trainer)
+        tid = self.man.tensor_ids(out.device)
+        _torch_weighted_avg(trainer.base, g, w, tid, out)
+        self._round += 1
+        return out
+
+    def broadcast_base(self, base: torch.Tensor, src: int = 0) -> None:
+        dist.broadcast(base, src=src, group=self.group)
+
+
+def _torch_weighted_avg(base, gathered, w, tid, out):
+    s = w.sum(0)
+    out.copy_(base * s[tid])
+    for i in range(gathered.shape[0]):
+        out.addcmul_(gathered[i].float(), w[i][tid])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# peer memory (the product path)
+# ---------------------------------------------------------------------------------------------------------------------
+class PeerExchange(Exchange):
+    """Symmetric-window exchange; see :mod:`.symm`.  Windows: delta (x2, round parity), fp8 scales, base (fp32 landing
+    buffer for the new averaged model), base16 (bf16 copy feeding the fused broadcast->GEMM path)."""
+
+    kind = "peer"
+
+    def __init__(self, manifest: Manifest, group=None, delta_dtype: str = "fp32", with_base16: bool = True):
+        from .symm import F_BASE, F_DELTA, SymmetricWindow
+
+        self.man = manifest
+        self.delta_dtype_name = delta_dtype
+        self.delta_dtype = DELTA_DTYPES[delta_dtype]
+        esz = torch.empty((), dtype=self.delta_dtype).element_size()
+        n = manifest.total
+        regions = {"delta0": n * esz, "delta1": n * esz, "base": n * 4}
+        if delta_dtype == "fp8":
+            regions.update({"scale0": n // 32 * 4, "scale1": n // 32 * 4})
+        if with_base16:
+            regions["base16"] = n * 2
+        self.win = SymmetricWindow(regions, group)
+        self.rank, self.world = self.win.rank, self.win.world
+        self.F_DELTA, self.F_BASE = F_DELTA, F_BASE
+        self.nan_flags = torch.zeros(max(self.world, 1), dtype=torch.int32, device=self.win.device)
+        self._base_round = 0
+        self.with_base16 = with_base16
+
+    # -- miner side -------------------------------------------------------------------------------------------------
+    def delta_buf(self, round: int, rank: Optional[int] = None) -> torch.Tensor:
+        name = f"delta{round & 1}"
+        return self.win.local(name, self.delta_dtype) if rank is None else self.win.peer(name, rank, self.delta_dtype)
+
+    def scale_buf(self, round: int, rank: Optional[int] = None) -> Optional[torch.Tensor]:
+        if self.delta_dtype_name != "fp8":
+            return None
+        name = f"scale{round & 1}"
+        return self.win.local(name, torch.float32) if rank is None else self.win.peer(name, rank, torch.float32)
+
+    def publish_delta(self, trainer, round: int, dst_ranks: Optional[List[int]] = None) -> None:
+        """Delta is written straight into this rank's window (no copies), then the round flag is release-stored."""
+        trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round))
+        self.win.publish(self.F_DELTA, round, dst_ranks)
+
+    def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
+        flags = self.win.flags()
+        if int(flags[self.F_DELTA + src].item()) < round:
+            return None  # stale flag == failed download in the reference
+        d = self.delta_buf(round, src)[:self.man.total]
+        if self.delta_dtype_name == "fp8":
+            return ops.dequant_fp8(d, self.scale_buf(round, src))
+        return d
+
+    # -- averager side ------------------------------------------------------------------------------------------------
+    def _delta_ptrs(self, round: int, miners: Sequence[int]) -> Tuple[List[int], Optional[List[int]]]:
+        name, sname = f"delta{round & 1}", f"scale{round & 1}"
+        d = [self.win.ptr(name, r) for r in miners]
+        s = [self.win.ptr(sname, r) for r in miners] if self.delta_dtype_name == "fp8" else None
+        return d, s
+
+    def gather_average(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int], out_f32,
+                       out_bf16=None, wait: bool = True) -> torch.Tensor:
+        """Pull form of fused kernel (a): this rank reads every miner's delta over NVLink and writes theta_new locally."""
+        d, s = self._delta_ptrs(round, miners)
+        wf = [self.win.flag_ptr(self.F_DELTA + r) for r in miners] if wait else None
+        self.nan_flags.zero_()
+        mode = {"fp32": 0, "bf16": 1, "fp8": 2}[self.delta_dtype_name]
+        return ops.weighted_avg(base, d, w, self.man, [out_f32], [out_bf16] if out_bf16 is not None else None, dscales=s,
+                                nan_flags=self.nan_flags, wait_flags=wf, wait_value=round, error_flag=self.win.error_flag,
+                                mode=mode)
+
+    def sharded_average_broadcast(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int]) -> torch.Tensor:
+        """Reduce-scatter + all-gather form: every rank reduces its shard of the arena from ALL miners' windows and
+        stores the result into EVERY rank's ``base`` window (and bf16 ``base16``) -- one kernel per rank, no NCCL.
+        Returns this rank's (complete, after the flag wait) fp32 base window."""
+        cs, _, _ = self.man.seg_table(base.device)
+        nchunks = cs.numel()
+        per = (nchunks + self.world - 1) // self.world
+        c0, c1 = min(nchunks, self.rank * per), min(nchunks, (self.rank + 1) * per)
+        d, s = self._delta_ptrs(round, miners)
+        wf = [self.win.flag_ptr(self.F_DELTA + r) for r in miners]
+        outs_f32 = [self.win.ptr("base", r) for r in range(self.world)]
+        outs_b16 = [self.win.ptr("base16", r) for r in range(self.world)] if self.with_base16 else None
+        self.nan_flags.zero_()
+        mode = {"fp32": 0, "bf16": 1, "fp8": 2}[self.delta_dtype_name]
+        ops.weighted_avg(base, d, w, self.man, outs_f32, outs_b16, dscales=s, nan_flags=self.nan_flags, wait_flags=wf,
+                         wait_value=round, error_flag=self.win.error_flag, chunk_range=(c0, c1), mode=mode)
+        self._base_round = round + 1
+        self.win.publish(self.F_BASE, self._base_round)
+        self.win.wait(self.F_BASE, self._base_round)
+        return self.win.local("base", torch.float32)[:self.man.total]
+
+    def publish_base(self, base: torch.Tensor, round: int, dst_ranks: Optional[List[int]] = None) -> None:
+        """Averager -> everyone: P2P stores of the fp32 base (+bf16 copy) into each rank's landing window, then flag."""
+        dst = list(range(self.world)) if dst_ranks is None else dst_ranks
+        n = self.man.total
+        for r in dst:
+            self.win.peer("base", r, torch.float32)[:n].copy_(base, non_blocking=True)
+            if self.with_base16:
+                self.win.peer("base16", r, torch.bfloat16)[:n].copy_(base, non_blocking=True)
+        self._base_round = round
+        self.win.publish(self.F_BASE, round, dst)
+
+    def base_round(self, src: int = 0) -> int:
+        return int(self.win.flags()[self.F_BASE + src].item())
+
+    def base_view(self) -> torch.Tensor:
+        return self.win.local("base", torch.float32)[:self.man.total]
+
+    def base16_ptr(self, rank: int) -> int:
+        return self.win.ptr("base16", rank)
+
+    def fetch_base(self, out: torch.Tensor) -> int:
+        out.copy_(self.base_view())
+        return self.base_round()

@@ -1,0 +1,155 @@
+"""Symmetric peer-memory windows over NVLink 5 / NVSwitch (one process per GPU).
+
+Each rank allocates one window with the C++ runtime (csrc/symm_runtime.cu: cudaMalloc + CUDA IPC), the handles are
+exchanged through the ``torch.distributed`` control plane, and every rank maps every peer's window.  Kernels then load
+from / store to the peer addresses directly (csrc/optim_avg.cu, csrc/sm100_gemm.cu), synchronised by release/acquire
+round flags that live inside the windows.
+
+This is the in-box replacement of the reference's tensor plane: ``torch.save`` -> git-lfs push -> ``hf_hub_download``
+-> ``torch.load`` (reference hivetrain/hf_manager.py:91-136,186-197) and of its SHA polling (:151-159).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _lib
+
+FLAG_BYTES = 4096
+FLAG_WORDS = FLAG_BYTES // 4
+# flag word layout (uint32 indices); each block has one slot per source rank (<= 64 ranks)
+F_DELTA = 0     # [F_DELTA + src]  = last delta round published by rank src
+F_BASE = 64     # [F_BASE + src]   = last base round pushed by averager-shard src
+F_BARRIER = 128  # [F_BARRIER + src] = barrier epoch
+F_HEART = 192   # [F_HEART + src]  = heartbeat counter
+
+
+class _CudaBuffer:
+    """Minimal ``__cuda_array_interface__`` carrier so torch can wrap a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.as_tensor(_CudaBuffer(ptr, nbytes), device=device)
+
+
+@dataclass
+class Region:
+    name: str
+    offset: int
+    nbytes: int
+
+
+class SymmetricWindow:
+    """One window per rank with named regions; identical layout on every rank (hence "symmetric")."""
+
+    def __init__(self, regions: Dict[str, int], group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+        assert torch.cuda.is_available(), "SymmetricWindow needs CUDA"
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        L = _lib.lib()
+        _lib.check(L.dtb_set_device(self.device.index), "dtb_set_device")
+        self.regions: Dict[str, Region] = {}
+        off = FLAG_BYTES
+        self.regions["flags"] = Region("flags", 0, FLAG_BYTES)
+        for name, nbytes in regions.items():
+            nbytes = (nbytes + 1023) // 1024 * 1024
+            self.regions[name] = Region(name, off, nbytes)
+            off += nbytes
+        self.nbytes = off
+        p = ctypes.c_void_p()
+        _lib.check(L.dtb_symm_alloc(ctypes.c_size_t(self.nbytes), ctypes.byref(p)), "dtb_symm_alloc")
+        self.local_ptr = p.value
+        self._local = tensor_from_ptr(self.local_ptr, self.nbytes, self.device)
+        self.peer_ptrs: List[int] = [0] * self.world
+        self.peer_ptrs[self.rank] = self.local_ptr
+        self.p2p = True
+        if self.world > 1:
+            h = ctypes.create_string_buffer(64)
+            _lib.check(L.dtb_ipc_get_handle(ctypes.c_void_p(self.local_ptr), h), "ipc_get_handle")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(h.raw), group=group)
+            for r, hr in enumerate(handles):
+                if r == self.rank:
+                    continue
+                q = ctypes.c_void_p()
+                rc = L.dtb_ipc_open_handle(ctypes.create_string_buffer(hr, 64), ctypes.byref(q))
+                if rc != 0:
+                    L.dtb_last_error()
+                    self.p2p = False
+                    raise RuntimeError(f"cudaIpcOpenMemHandle(rank {r}) failed with {rc}; peer windows unavailable")
+                self.peer_ptrs[r] = q.value
+            dist.barrier(group=group)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._epoch = 0
+
+    # -- addressing ------------------------------------------------------------------------------------------------
+    def ptr(self, region: str, rank: Optional[int] = None, byte_offset: int = 0) -> int:
+        r = self.rank if rank is None else rank
+        return self.peer_ptrs[r] + self.regions[region].offset + byte_offset
+
+    def local(self, region: str, dtype=torch.uint8) -> torch.Tensor:
+        reg = self.regions[region]
+        return self._local[reg.offset:reg.offset + reg.nbytes].view(dtype)
+
+    def peer(self, region: str, rank: int, dtype=torch.uint8) -> torch.Tensor:
+        """Tensor view over a PEER's region (loads/stores by torch ops travel over NVLink)."""
+        reg = self.regions[region]
+        if rank == self.rank:
+            return self.local(region, dtype)
+        return tensor_from_ptr(self.peer_ptrs[rank] + reg.offset, reg.nbytes, self.device).view(dtype)
+
+    def flag_ptr(self, word: int, rank: Optional[int] = None) -> int:
+        return self.ptr("flags", rank, 4 * word)
+
+    def flags(self) -> torch.Tensor:
+        return self.local("flags", torch.int32)
+
+    # -- synchronisation -------------------------------------------------------------------------------------------
+    def publish(self, block: int, value: int, dst_ranks: Optional[List[int]] = None) -> None:
+        """After all prior work on the current stream: release-store ``value`` into slot [block + my_rank] of every
+        destination rank's flag page (csrc/optim_avg.cu publish_flag_kernel)."""
+        dst = list(range(self.world)) if dst_ranks is None else dst_ranks
+        arr = (ctypes.c_void_p * len(dst))(*[self.flag_ptr(block + self.rank, r) for r in dst])
+        _lib.check(_lib.lib().dtb_publish_flag(arr, len(dst), ctypes.c_uint32(value), _lib.stream_ptr()), "publish_flag")
+
+    def wait(self, block: int, value: int, src_ranks: Optional[List[int]] = None) -> None:
+        """Stream-ordered wait (device-side spin) until slot [block + src] >= value for every src."""
+        src = list(range(self.world)) if src_ranks is None else src_ranks
+        if src == list(range(src[0], src[0] + len(src))):
+            _lib.check(_lib.lib().dtb_wait_flags(ctypes.c_void_p(self.flag_ptr(block + src[0])), len(src), 1,
+                                                 ctypes.c_uint32(value), _lib.ptr(self.error_flag), _lib.stream_ptr()),
+                       "wait_flags")
+        else:
+            for s in src:
+                _lib.check(_lib.lib().dtb_wait_flags(ctypes.c_void_p(self.flag_ptr(block + s)), 1, 1, ctypes.c_uint32(value),
+                                                     _lib.ptr(self.error_flag), _lib.stream_ptr()), "wait_flags")
+
+    def device_barrier(self) -> None:
+        """All ranks' streams rendezvous on the device (no host sync, no NCCL)."""
+        self._epoch += 1
+        self.publish(F_BARRIER, self._epoch)
+        self.wait(F_BARRIER, self._epoch)
+
+    def check_errors(self) -> None:
+        if int(self.error_flag.item()) != 0:
+            raise RuntimeError("peer flag wait timed out (a rank stalled or died)")
+
+    def close(self) -> None:
+        L = _lib.lib()
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank and p:
+                L.dtb_ipc_close_handle(ctypes.c_void_p(p))
+        if self.local_ptr:
+            del self._local
+            L.dtb_symm_free(ctypes.c_void_p(self.local_ptr))
+            self.local_ptr = 0

@@ -1,0 +1,267 @@
+"""Numerics of every hand-written sm_100a kernel against the plain-PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+from distributedtraining_b200 import ops
+from distributedtraining_b200.ops import reference as ref
+from distributedtraining_b200.models.arena import Manifest
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).bfloat16()
+
+
+def _close(a, b, rtol=2e-2, atol=None):
+    a, b = a.float(), b.float()
+    atol = atol if atol is not None else rtol * max(b.abs().max().item(), 1e-6)
+    err = (a - b).abs().max().item()
+    assert err <= atol, f"max err {err} > {atol}"
+
+
+def test_kernels_loaded():
+    assert ops.have_kernels()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(256, 512, 192, 0, 0), (300, 1000, 200, 0, 0), (512, 768, 512, 0, 1),
+                                             (768, 512, 640, 1, 1), (256, 512, 512, 1, 0)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    torch.manual_seed(0)
+    A, B = _bf(M, K, scale=0.5), _bf(N, K, scale=0.5)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, out, a_mn=bool(a_mn), b_mn=bool(b_mn))
+    _close(out, A.float() @ B.float().t(), rtol=1e-2)
+
+
+@pytest.mark.parametrize("epi", ["bias", "bias_gelu", "bias_resid", "resid", "dgelu"])
+def test_gemm_epilogues(epi):
+    torch.manual_seed(1)
+    M, N, K = 384, 768, 256
+    A, B = _bf(M, K, scale=0.5), _bf(N, K, scale=0.5)
+    bias, aux = _bf(N), _bf(M, N)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.empty_like(out)
+    r = torch.empty(M, N, device=DEV)
+    r2 = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2 if epi == "bias_gelu" else None)
+    ref.gemm(A, B, r, epi=epi, bias=bias, aux=aux, out2=r2)
+    _close(out, r, rtol=1e-2)
+    if epi == "bias_gelu":
+        _close(out2, r2, rtol=1e-2)
+
+
+def test_gemm_f32_accumulate_splitk():
+    torch.manual_seed(2)
+    M, N, K = 768, 768, 4096
+    A, B = _bf(M, K, scale=0.3), _bf(N, K, scale=0.3)
+    a, b = A.t().contiguous(), B.t().contiguous()
+    out = torch.ones(M, N, device=DEV)
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, accumulate=True, splits=8)
+    _close(out, 1.0 + A.float() @ B.float().t(), rtol=1e-4)
+
+
+def test_gemm_strided_views_vocab():
+    torch.manual_seed(3)
+    M, V, d, ldl = 256, 1003, 128, 1024
+    x, wte = _bf(M, d), _bf(V, d)
+    lg = torch.zeros(M, ldl, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, wte, lg[:, :V])
+    _close(lg[:, :V], x.float() @ wte.float().t(), rtol=1e-2)
+    assert lg[:, V:].abs().max().item() == 0.0
+    dx = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(lg[:, :V], wte, dx, b_mn=True)
+    _close(dx, lg[:, :V].float() @ wte.float(), rtol=1e-2)
+    dw = torch.zeros(V, d, device=DEV)
+    ops.gemm(lg[:, :V], x, dw, a_mn=True, b_mn=True, accumulate=True)
+    _close(dw, lg[:, :V].float().t() @ x.float(), rtol=1e-3)
+
+
+def test_embed():
+    torch.manual_seed(4)
+    B, T, V, d = 4, 32, 1000, 256
+    ids = torch.randint(0, V, (B, T), device=DEV, dtype=torch.int32)
+    wte, wpe = _bf(V, d), _bf(64, d)
+    out = torch.empty(B * T, d, device=DEV, dtype=torch.bfloat16)
+    ops.embed_fwd(ids, wte, wpe, out)
+    r = torch.empty(B * T, d, device=DEV)
+    ref.embed_fwd(ids.long(), wte, wpe, r)
+    _close(out, r, rtol=1e-2)
+    dx = _bf(B * T, d)
+    dwte, dwpe = torch.zeros(V, d, device=DEV), torch.zeros(64, d, device=DEV)
+    rwte, rwpe = torch.zeros(V, d, device=DEV), torch.zeros(64, d, device=DEV)
+    ops.embed_bwd(dx, ids, dwte, dwpe)
+    ref.embed_bwd(dx, ids.long(), rwte, rwpe)
+    _close(dwte, rwte, rtol=1e-4)
+    _close(dwpe, rwpe, rtol=1e-4)
+
+
+@pytest.mark.parametrize("rms", [False, True])
+@pytest.mark.parametrize("d", [768, 2048])
+def test_norm(rms, d):
+    torch.manual_seed(5)
+    M = 515
+    x, w, b = _bf(M, d) + 0.3, _bf(d) + 1.0, _bf(d)
+    out = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    rout, rmean, rrstd = torch.empty(M, d, device=DEV), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    if rms:
+        ops.rmsnorm_fwd(x, w, 1e-5, out, rstd)
+        ref.rmsnorm_fwd(x, w, 1e-5, rout, rrstd)
+    else:
+        ops.layernorm_fwd(x, w, b, 1e-5, out, mean, rstd)
+        ref.layernorm_fwd(x, w, b, 1e-5, rout, rmean, rrstd)
+        _close(mean, rmean, rtol=1e-3)
+    _close(out, rout, rtol=1e-2)
+    _close(rstd, rrstd, rtol=1e-3)
+    dy, dres = _bf(M, d), _bf(M, d)
+    dx = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    dw, db = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    rdx, rdw, rdb = torch.empty(M, d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    if rms:
+        ops.rmsnorm_bwd(dy, x, w, rrstd, dx, dw, dres)
+        ref.rmsnorm_bwd(dy, x, w, rrstd, rdx, rdw, dres)
+    else:
+        ops.layernorm_bwd(dy, x, w, rmean, rrstd, dx, dw, db, dres)
+        ref.layernorm_bwd(dy, x, w, rmean, rrstd, rdx, rdw, rdb, dres)
+        _close(db, rdb, rtol=1e-3)
+    _close(dx, rdx, rtol=1e-2)
+    _close(dw, rdw, rtol=1e-3)
+
+
+def test_cross_entropy():
+    torch.manual_seed(6)
+    M, V, ldl = 64, 50258, 50304
+    lg = torch.zeros(M, ldl, device=DEV, dtype=torch.bfloat16)
+    lg[:, :V] = _bf(M, V, scale=2.0)
+    tgt = torch.randint(0, V, (M,), device=DEV, dtype=torch.int32)
+    tgt[::7] = -1
+    r = lg.clone().float()
+    losses, rl = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ref.ce_fwd_bwd(r, tgt, V, rl, 1.0 / M)
+    ops.ce_fwd_bwd(lg, tgt, V, losses, 1.0 / M)
+    _close(losses, rl, rtol=1e-3)
+    _close(lg[:, :V], r[:, :V], rtol=2e-2)
+    assert lg[:, V:].abs().max().item() == 0.0
+
+
+def test_colsum_swiglu_rope():
+    torch.manual_seed(7)
+    x = _bf(1000, 768)
+    out, r = torch.ones(768, device=DEV), torch.ones(768, device=DEV)
+    ops.colsum(x, out)
+    ref.colsum(x, r)
+    _close(out, r, rtol=1e-4)
+    gu = _bf(333, 512)
+    o, ro = torch.empty(333, 256, device=DEV, dtype=torch.bfloat16), torch.empty(333, 256, device=DEV)
+    ops.swiglu_fwd(gu, o)
+    ref.swiglu_fwd(gu, ro)
+    _close(o, ro, rtol=1e-2)
+    d = _bf(333, 256)
+    dg, rdg = torch.empty_like(gu), torch.empty(333, 512, device=DEV)
+    ops.swiglu_bwd(d, gu, dg)
+    ref.swiglu_bwd(d, gu, rdg)
+    _close(dg, rdg, rtol=1e-2)
+    B, T, H, Hkv, hd = 2, 64, 4, 2, 64
+    qkv = _bf(B * T, (H + 2 * Hkv) * hd)
+    q2 = qkv.clone().float()
+    ops.rope_(qkv, B, T, H, Hkv, hd, 10000.0)
+    ref.rope_(q2, B, T, H, Hkv, hd, 10000.0)
+    _close(qkv, q2, rtol=1e-2)
+
+
+def _toy_manifest():
+    return Manifest([("a", (300, 70), "normal", True), ("b", (70,), "zeros", False), ("c", (1000, 33), "normal", True),
+                     ("d", (5,), "ones", False)])
+
+
+def test_adamw_delta_reset():
+    torch.manual_seed(8)
+    n = 256 * 40
+    master = torch.randn(n, device=DEV)
+    base = master.clone()
+    grad = torch.randn(n, device=DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    rm, rmm, rv = master.clone(), m.clone(), v.clone()
+    st = ops.AdamState(DEV, 5e-4, eps=1e-6)
+    for step in range(1, 4):
+        ops.adamw_step(master, p16, grad, m, v, st)
+        ref.adamw_step(rm, None, grad, rmm, rv, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, step=step)
+    _close(master, rm, rtol=1e-5)
+    _close(p16, rm, rtol=1e-2)
+    assert int(st.step.item()) == 3
+    for dt in (torch.float32, torch.bfloat16):
+        d = torch.empty(n, device=DEV, dtype=dt)
+        ops.delta_emit(master, base, d)
+        _close(d, master - base, rtol=1e-2 if dt == torch.bfloat16 else 1e-6)
+    q, sc = torch.empty(n, device=DEV, dtype=torch.uint8), torch.empty(n // 32, device=DEV)
+    ops.delta_emit(master, base, q, sc)
+    _close(ops.dequant_fp8(q, sc), master - base, rtol=7e-2)
+    ops.round_reset(base, master, p16, m, v)
+    assert torch.equal(master, base) and m.abs().max().item() == 0 and v.abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp8"])
+def test_weighted_avg_multi_dot(dtype):
+    torch.manual_seed(9)
+    man = _toy_manifest()
+    n, P, N = man.total, len(man), 5
+    base = torch.randn(n, device=DEV)
+    true = [torch.randn(n, device=DEV) * 0.1 for _ in range(N)]
+    w = torch.rand(N, P, device=DEV) - 0.2
+    scales = None
+    if dtype == "fp32":
+        deltas = true
+    elif dtype == "bf16":
+        deltas = [t.bfloat16() for t in true]
+    else:
+        deltas, scales = [], []
+        for t in true:
+            q, sc = torch.empty(n, device=DEV, dtype=torch.uint8), torch.empty(n // 32, device=DEV)
+            ops.delta_emit(t, torch.zeros_like(t), q, sc)
+            deltas.append(q)
+            scales.append(sc)
+    dec = [ops.dequant_fp8(d, s) for d, s in zip(deltas, scales)] if scales else [d.float() for d in deltas]
+    out, out16 = torch.empty(n, device=DEV), torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    nan = torch.zeros(N, device=DEV, dtype=torch.int32)
+    ops.weighted_avg(base, deltas, w, man, [out], [out16], dscales=scales, nan_flags=nan)
+    r = torch.empty(n, device=DEV)
+    ref.weighted_avg(base, dec, w, man.tensor_ids(DEV), r)
+    _close(out, r, rtol=1e-5)
+    _close(out16, r, rtol=1e-2)
+    assert nan.sum().item() == 0
+    # == the reference's formulation sum_i w_ij (base + delta_i)
+    tid = man.tensor_ids(DEV)
+    direct = sum(w[i][tid] * (base + dec[i]) for i in range(N))
+    _close(out, direct, rtol=1e-5)
+    # shard form: two launches over disjoint chunk ranges give the same result
+    cs, _, _ = man.seg_table(DEV)
+    out2 = torch.zeros(n, device=DEV)
+    half = cs.numel() // 2
+    ops.weighted_avg(base, deltas, w, man, [out2], dscales=scales, chunk_range=(0, half))
+    ops.weighted_avg(base, deltas, w, man, [out2], dscales=scales, chunk_range=(half, cs.numel()))
+    assert torch.equal(out2, out)
+    g = torch.randn(n, device=DEV)
+    G, rG = torch.empty(N, P, device=DEV), torch.empty(N, P, device=DEV)
+    ops.multi_dot(g, deltas, base, out, man, G, dscales=scales)
+    ref.multi_dot(g, dec, base, out, tid, P, rG)
+    _close(G, rG, rtol=1e-3)
+
+
+def test_weighted_avg_nan_screen():
+    man = _toy_manifest()
+    n, P, N = man.total, len(man), 3
+    base = torch.zeros(n, device=DEV)
+    deltas = [torch.zeros(n, device=DEV) for _ in range(N)]
+    deltas[1][man["c"].offset + 17] = float("nan")
+    w = torch.full((N, P), 1.0 / N, device=DEV)
+    nan = torch.zeros(N, device=DEV, dtype=torch.int32)
+    out = torch.empty(n, device=DEV)
+    ops.weighted_avg(base, deltas, w, man, [out], nan_flags=nan)
+    assert nan.tolist() == [0, 1, 0]
