@@ -203,6 +203,78 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
   }
 }
 
+// Fast path (d = VPL * 256): per-lane column partials for dw/db stay in REGISTERS across all rows of the warp and are
+// flushed once per warp (shared-memory atomics) and once per block (global atomics).
+template <bool RMS, int VPL>
+__global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const bf16* __restrict__ dresid,
+                                                            bf16* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db, int M) {
+  constexpr int d = VPL * 256;
+  extern __shared__ float sm[];  // [2][d]
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float ww[VPL][8], adw[VPL][8], adb[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(w) + lane + 32 * j), ww[j]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) adw[j][k] = adb[j][k] = 0.f;
+  }
+  for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * d);
+    const float mu = RMS ? 0.f : mean[row];
+    const float rs = rstd[row];
+    float g[VPL][8], xh[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      unpack8(__ldg(dyr + lane + 32 * j), g[j]);
+      unpack8(__ldg(xr + lane + 32 * j), xh[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xh[j][k] = (xh[j][k] - mu) * rs;
+        adw[j][k] += g[j][k] * xh[j][k];
+        if (!RMS) adb[j][k] += g[j][k];
+        g[j][k] *= ww[j][k];
+        s1 += g[j][k];
+        s2 += g[j][k] * xh[j][k];
+      }
+    }
+    s1 = RMS ? 0.f : warp_sum(s1) * (1.f / d);
+    s2 = warp_sum(s2) * (1.f / d);
+    uint4* o = reinterpret_cast<uint4*>(dx + size_t(row) * d);
+    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      float r[8];
+      if (rr) unpack8(__ldg(rr + lane + 32 * j), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = (g[j][k] - s1 - xh[j][k] * s2) * rs;
+        if (rr) v += r[k];
+        g[j][k] = v;
+      }
+      o[lane + 32 * j] = pack8(g[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm[(lane + 32 * j) * 8 + k], adw[j][k]);
+      if (!RMS) atomicAdd(&sm[d + (lane + 32 * j) * 8 + k], adb[j][k]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(&dw[i], sm[i]);
+    if (!RMS && db) atomicAdd(&db[i], sm[d + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // fused cross-entropy: one CTA per row; the row is pulled into shared memory once (<= ~100 KB for V = 50k bf16),
 // loss = lse - logit[target]; logits are overwritten in place with (softmax - onehot) * scale.
@@ -394,10 +466,25 @@ extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* o
   else norm_fwd_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)out, mean, rstd, M, d, eps);
   return KCHECK();
 }
+template <bool RMS, int VPL>
+static void launch_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                                 const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s) {
+  const size_t smem = size_t(2) * VPL * 256 * sizeof(float);
+  norm_bwd_fast_kernel<RMS, VPL><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
+                                                         (const bf16*)dresid, (bf16*)dx, dw, db, M);
+}
 extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                             const void* dresid, void* dx, float* dw, float* db, int M, int d, int rms, int num_sms,
                             cudaStream_t s) {
   const int grid = min((M + 7) / 8, num_sms * 2);
+#define FAST(V)                                                                                             \
+  if (d == V * 256 && (rms || V < 8)) {                                                                     \
+    if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s);            \
+    else launch_norm_bwd_fast<false, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s);               \
+    return KCHECK();                                                                                        \
+  }
+  FAST(3) FAST(4) FAST(8)
+#undef FAST
   const size_t smem = size_t(2) * d * sizeof(float);
   if (rms) {
     static bool cfg = false;

@@ -86,7 +86,7 @@ class ModuleTrainer:
         self.steps_done = 0
         self.cfg = None
 
-    def loss_and_grad(self, batch, zero_grad: bool = True) -> torch.Tensor:
+    def loss_and_grad(self, batch, labels=None, zero_grad: bool = True) -> torch.Tensor:
         if zero_grad:
             self.grad.zero_()
         loss = self.loss_fn(self.module, batch)

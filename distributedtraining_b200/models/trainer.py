@@ -57,7 +57,10 @@ class Trainer:
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimizer step on a [B,T] batch (host-pinned or device).  Returns the device-resident mean loss."""
+        if isinstance(input_ids, dict):
+            input_ids, labels = input_ids["input_ids"], None  # miner: labels = input_ids (PAD not masked)
         self.engine.set_batch(input_ids, labels)
+        assert self.engine.n_rows == self.batch, "training batches must fill the static batch"
         if not self.use_graph:
             c0 = ops.launch_count()
             loss = self._step_body()
@@ -87,8 +90,18 @@ class Trainer:
         self.steps_done += 1
         return loss
 
+    def loss_and_grad(self, input_ids, labels: Optional[torch.Tensor] = None, zero_grad: bool = True) -> torch.Tensor:
+        """Forward + backward at the CURRENT master/p16 without an optimizer step: grads land in ``self.grad``.
+        (The averager's meta-learning needs dL/dtheta_bar: reference hivetrain/averaging_logic.py:502-511.)"""
+        if isinstance(input_ids, dict):
+            input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
+        self.engine.set_batch(input_ids, labels)
+        return self.engine.forward_backward(zero_grad)
+
     @torch.no_grad()
     def eval_loss(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if isinstance(input_ids, dict):
+            input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
         self.engine.set_batch(input_ids, labels)
         return self.engine.forward_loss()
 

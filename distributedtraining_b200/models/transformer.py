@@ -294,6 +294,7 @@ class TransformerEngine:
         self.dact = mk(M, Fd) if glu else None
         self.targets = torch.full((batch, seq), -1, dtype=torch.int32, device=self.dev)
         self.ids = torch.zeros((batch, seq), dtype=torch.int32, device=self.dev)
+        self.n_rows = batch
 
     # -- helpers ---------------------------------------------------------------------------------------------------
     def _norm_fwd(self, x, w, b, out, mean, rstd):
@@ -309,11 +310,18 @@ class TransformerEngine:
             ops.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
 
     def set_batch(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
-        """Copy a batch into the static id/target buffers (non-blocking when the source is pinned)."""
-        self.ids.copy_(input_ids.view(self.B, self.T), non_blocking=True)
-        tgt = self.targets
-        src = self.ids if labels is None else labels.view(self.B, self.T)
-        tgt[:, :-1].copy_(src[:, 1:], non_blocking=True)
+        """Copy a batch into the static id/target buffers (non-blocking when the source is pinned).  A batch with fewer
+        than B rows (last eval batch) is padded with ignored rows; the loss is normalised by the real row count."""
+        ids2 = input_ids.view(-1, self.T)
+        n = ids2.shape[0]
+        assert n <= self.B, f"batch of {n} rows exceeds the engine's static batch {self.B}"
+        self.n_rows = n
+        src = ids2 if labels is None else labels.view(-1, self.T)
+        if n < self.B:
+            self.ids[n:].zero_()
+            self.targets[n:].fill_(-1)
+        self.ids[:n].copy_(ids2, non_blocking=True)
+        self.targets[:n, :-1].copy_(src[:, 1:], non_blocking=True)
 
     # -- forward ---------------------------------------------------------------------------------------------------
     def forward(self, train: bool = True) -> None:
@@ -342,7 +350,7 @@ class TransformerEngine:
     def _lm_head(self, backward: bool) -> None:
         cfg, P = self.cfg, self.P
         V = cfg.vocab_size
-        n_valid = self.B * (self.T - 1)
+        n_valid = self.n_rows * (self.T - 1)
         scale = 1.0 / max(n_valid, 1)
         tgt = self.targets.view(-1)
         for c0 in range(0, self.M, self.lm_chunk):

@@ -1,0 +1,230 @@
+"""Validator role: score every miner's delta by the loss / perplexity drop it produces on held-out data.
+
+Reference: hivetrain/validation_logic.py -- ``ModelValidator`` (:29-203), ``DeltaValidator`` (:251-259),
+``LocalValidator`` / ``LocalDeltaValidator`` (:206-262), ``MNISTValidator`` / ``MNISTDeltaValidator`` (:265-318).
+Algorithm spec: SURVEY.md section 2.6-B.
+
+B200-first differences (scores are computed by the same formulas):
+* ``theta_base`` is never mutated: ``theta_base + delta_i`` is materialised by ONE fused kernel straight into the
+  engine's (fp32 master, bf16 compute) arenas -- reading the delta from the miner's peer window over NVLink -- so the
+  reference's ``deepcopy(state_dict)`` / ``load_state_dict`` per miner (:123,139) and its sha256-on-CPU round trip
+  (:133) disappear;
+* the base loss is re-evaluated whenever the base changes (the reference computes it once in the constructor and never
+  refreshes it, :48);
+* ``sum(ppl_score) == 0`` no longer divides by zero (:186-187).
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import ops
+from .training_manager import calculate_model_hash
+from .utils.logging import MetricsLogger, logger
+
+
+def _batch_ids_labels(batch):
+    if isinstance(batch, dict):
+        return batch["input_ids"], batch.get("labels")
+    return batch, None
+
+
+class ModelValidator:
+    def __init__(self, device, model, optimizer=None, data_loader: Optional[Iterable] = None, bittensor_network=None,
+                 hf_manager=None, interval: float = 3600, chain_manager=None, check_update_interval: float = 300,
+                 metrics: Optional[MetricsLogger] = None, compute_hash: bool = False, max_rounds: Optional[int] = None):
+        self.device = device
+        self.model = model  # Trainer / ModuleTrainer; model.base is theta_base
+        self.optimizer = optimizer  # accepted for signature parity; the validator never steps it
+        self.data_loader = data_loader
+        self.bittensor_network = bittensor_network
+        self.hf_manager = hf_manager
+        self.chain_manager = chain_manager
+        self.interval = interval
+        self.check_update_interval = check_update_interval
+        self.last_pull_time = 0.0
+        self.metrics = metrics or MetricsLogger(None, "validator")
+        self.compute_hash = compute_hash
+        self.max_rounds = max_rounds
+        self.base_loss, self.base_perplexity = self.evaluate_model()
+        hotkeys = list(bittensor_network.metagraph.hotkeys) if bittensor_network is not None else []
+        self.scores = {hk: 0.0 for hk in hotkeys}
+        self.normalized_scores = {hk: 0.0 for hk in hotkeys}
+        self.loss_scores = {hk: 0.0 for hk in hotkeys}
+        self.losses: Dict[str, float] = {}
+
+    # -- delta application ------------------------------------------------------------------------------------------
+    def update_model_weights(self, gradients, alpha: float = 5e-4) -> None:
+        """Gradient-style update theta -= alpha * g (reference :72-76).  ``gradients``: flat tensor or name->tensor."""
+        g = self._as_flat(gradients)
+        self.model.master.add_(g.to(self.model.master.device, torch.float32), alpha=-alpha)
+        self._sync_compute_copy()
+
+    def _as_flat(self, t) -> torch.Tensor:
+        if isinstance(t, dict):
+            return self.model.man.pack(t, torch.zeros(self.model.man.total, dtype=torch.float32))
+        return t
+
+    def _sync_compute_copy(self) -> None:
+        m = self.model
+        if getattr(m, "is_cuda", False) and m.p16.data_ptr() != m.master.data_ptr():
+            ops.cast_copy(m.master, m.p16)
+
+    def restore_base(self) -> None:
+        m = self.model
+        ops.round_reset(m.base, m.master, m.p16 if getattr(m, "is_cuda", False) else None, m.m, m.v, reset_moments=False)
+
+    # -- evaluation -------------------------------------------------------------------------------------------------------
+    def evaluate_model(self, metric: str = "loss") -> Tuple[float, float]:
+        """Mean CE over the eval set (batch-size weighted mean of per-batch means, reference :78-97) and exp() of it."""
+        total = torch.zeros((), dtype=torch.float64)
+        n = 0
+        acc = None
+        for batch in self.data_loader or []:
+            ids, labels = _batch_ids_labels(batch)
+            bs = ids.shape[0] if hasattr(ids, "shape") else len(ids[0])
+            loss = self.model.eval_loss(ids, labels)
+            acc = loss.detach().double() * bs if acc is None else acc + loss.detach().double() * bs  # stays on device
+            n += bs
+        if acc is None:
+            return float("nan"), float("nan")
+        avg = float(acc) / max(n, 1)  # ONE host read per evaluation (the reference syncs every batch)
+        return avg, math.exp(min(avg, 50.0))
+
+    def calculate_model_hash(self) -> str:
+        return calculate_model_hash(self.model)
+
+    # -- the scoring round ------------------------------------------------------------------------------------------------
+    def _maybe_pull(self) -> bool:
+        if self.hf_manager is None or time.time() - self.last_pull_time < self.check_update_interval:
+            return False
+        self.last_pull_time = time.time()
+        if self.hf_manager.check_for_new_submissions(self.hf_manager.model_repo_id):
+            logger.info("Averaged model updated. Pulling latest model...")
+            self.hf_manager.pull_latest_model()
+            self.model = self.hf_manager.update_model(self.model, reset_optimizer=False)
+            self.base_loss, self.base_perplexity = self.evaluate_model()  # refresh (reference never does)
+            return True
+        return False
+
+    def _receive(self, hotkey: str):
+        repo = self.chain_manager.retrieve_hf_repo(hotkey) if self.chain_manager is not None else hotkey
+        if repo is None:
+            return None
+        return self.hf_manager.receive_flat(repo) if hasattr(self.hf_manager, "receive_flat") else \
+            self.hf_manager.receive_gradients(repo)
+
+    def validate_and_score(self) -> Dict[str, float]:
+        net = self.bittensor_network
+        net.sync(lite=True)
+        self._maybe_pull()
+        logger.info(f"Base loss {self.base_loss:.4f} ppl {self.base_perplexity:.3f}")
+        for uid, hotkey in enumerate(net.metagraph.hotkeys):
+            delta = self._receive(hotkey)
+            if delta is not None and self._finite(delta):
+                try:
+                    self.update_model_weights(delta)
+                    if self.compute_hash:
+                        logger.info(f"Model hash is: {self.calculate_model_hash()}")
+                    loss, perplexity = self.evaluate_model()
+                    loss_score = max(0.0, self.base_loss - loss)
+                    perplexity_score = max(0.0, self.base_perplexity - perplexity)
+                finally:
+                    self.restore_base()
+            else:
+                loss, perplexity, loss_score, perplexity_score = float("nan"), float("nan"), 0.0, 0.0
+            self.losses[hotkey] = loss
+            self.loss_scores[hotkey] = loss_score
+            self.scores[hotkey] = perplexity_score
+            net.metrics_data[hotkey] = {"loss": loss if loss == loss else 1e9}
+            self.metrics.log(hotkey=hotkey, loss=loss, perplexity=perplexity, loss_score=loss_score,
+                             perplexity_score=perplexity_score)
+            logger.info(f"uid {uid} {hotkey}: loss {loss:.4f} ppl {perplexity:.3f} loss_score {loss_score:.4f} "
+                        f"ppl_score {perplexity_score:.4f}")
+        total = sum(self.scores.values())
+        self.normalized_scores = {hk: (max(0.0, sc / total) if total > 0 else 0.0) for hk, sc in self.scores.items()}
+        if net.should_set_weights():
+            net.set_weights(self.normalized_scores)
+        return self.normalized_scores
+
+    @staticmethod
+    def _finite(delta) -> bool:
+        if isinstance(delta, dict):
+            return all(bool(torch.isfinite(v).all()) for v in delta.values())
+        return bool(torch.isfinite(delta.float()).all()) if delta.dtype != torch.uint8 else True
+
+    def start_periodic_validation(self) -> None:
+        rounds = 0
+        while True:
+            t0 = time.time()
+            self.validate_and_score()
+            if self.hf_manager is not None:
+                self.hf_manager.clear_hf_cache()
+            rounds += 1
+            if self.max_rounds is not None and rounds >= self.max_rounds:
+                return
+            time.sleep(max(0.0, self.interval - (time.time() - t0)))
+
+
+class DeltaValidator(ModelValidator):
+    """theta <- delta + theta (reference :251-259), fused: one kernel writes base+delta into master AND the bf16 copy."""
+
+    def update_model_weights(self, weight_deltas, alpha: float = 5e-4) -> None:
+        m = self.model
+        d = self._as_flat(weight_deltas)
+        if getattr(m, "is_cuda", False) and isinstance(d, torch.Tensor) and d.is_cuda:
+            w = torch.ones(1, len(m.man), dtype=torch.float32, device=m.master.device)
+            ops.weighted_avg(m.base, [d], w, m.man, [m.master], [m.p16])  # N = 1, w = 1: theta_base + delta
+        else:
+            m.master.copy_(m.base + d.to(m.master.device, torch.float32))
+            self._sync_compute_copy()
+
+
+class LocalValidator(ModelValidator):
+    """Deltas come from a local directory tree ``<repo>/gradients.pt`` (reference :206-248)."""
+
+    def _receive(self, hotkey: str):
+        import os
+        repo = self.chain_manager.retrieve_hf_repo(hotkey) if self.chain_manager is not None else hotkey
+        if repo is None:
+            return None
+        path = os.path.join(str(repo), "gradients.pt")
+        if os.path.exists(path):
+            try:
+                return torch.load(path, map_location="cpu", weights_only=False)
+            except Exception as e:
+                logger.warning(f"Error loading gradients from {path}: {e}")
+                return None
+        return self.hf_manager.receive_flat(repo) if self.hf_manager is not None else None
+
+
+class LocalDeltaValidator(DeltaValidator, LocalValidator):
+    pass
+
+
+class MNISTValidator(LocalValidator):
+    """Accuracy-aware evaluation for (images, labels) batches (reference :265-310)."""
+
+    def evaluate_model(self, metric: str = "loss") -> Tuple[float, float]:
+        mod = self.model.module
+        was = mod.training
+        mod.eval()
+        tot, correct, n = 0.0, 0, 0
+        with torch.no_grad():
+            for x, y in self.data_loader or []:
+                x, y = x.to(self.device), y.to(self.device)
+                out = mod(x)
+                tot += float(torch.nn.functional.cross_entropy(out, y, reduction="sum"))
+                correct += int((out.argmax(1) == y).sum())
+                n += y.numel()
+        mod.train(was)
+        self.accuracy = correct / max(n, 1)
+        avg = tot / max(n, 1)
+        return avg, math.exp(min(avg, 50.0))
+
+
+class MNISTDeltaValidator(DeltaValidator, MNISTValidator):
+    pass

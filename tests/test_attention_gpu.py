@@ -1,0 +1,36 @@
+"""tcgen05 attention kernels vs the fp32 PyTorch reference (forward, LSE, and all three input gradients)."""
+import pytest
+import torch
+
+from distributedtraining_b200 import ops
+from distributedtraining_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,T,H,Hkv", [(4, 64, 2, 2), (2, 128, 3, 3), (2, 256, 2, 2), (1, 512, 4, 2), (3, 192, 2, 1),
+                                       (5, 64, 12, 12), (1, 1024, 2, 2), (3, 96, 2, 2)])
+def test_attention_fwd_bwd(B, T, H, Hkv):
+    torch.manual_seed(0)
+    hd = 64
+    M = B * T
+    qkv = (torch.randn(M, (H + 2 * Hkv) * hd, device="cuda") * 0.7).bfloat16()
+    out = torch.zeros(M, H * hd, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device="cuda")
+    ops.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv)
+    r_out = torch.empty(M, H * hd, device="cuda")
+    r_lse = torch.empty(B, H, T, device="cuda")
+    ref.attention_fwd(qkv, r_out, r_lse, B, T, H, hd, Hkv)
+    assert (out.float() - r_out).abs().max().item() < 2e-2 * max(1.0, r_out.abs().max().item())
+    assert (lse - r_lse).abs().max().item() < 2e-2
+    dout = (torch.randn(M, H * hd, device="cuda") * 0.5).bfloat16()
+    dqkv = torch.zeros_like(qkv)
+    ops.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)
+    r_dqkv = torch.empty(M, (H + 2 * Hkv) * hd, device="cuda")
+    ref.attention_bwd(dout, qkv, r_out.bfloat16(), r_lse, r_dqkv, B, T, H, hd, Hkv)
+    names = ["dq", "dk", "dv"]
+    parts = [H * hd, Hkv * hd, Hkv * hd]
+    for name, a, b in zip(names, dqkv.float().split(parts, dim=1), r_dqkv.split(parts, dim=1)):
+        rel = (a - b).norm() / (b.norm() + 1e-8)
+        assert rel < 3e-2, (name, float(rel))
+        assert (a - b).abs().max().item() < 5e-2 * max(1.0, b.abs().max().item()), name
