@@ -1,0 +1,228 @@
+#!/usr/bin/env python
+"""Headline benchmark (driver contract): local-SGD / delta-averaging training of GPT-2-small on N B200 GPUs of one node.
+
+Metric (BASELINE.json): tokens/sec (whole job; per-miner = value / N) and avg-round wall-time, device-timed, max over
+ranks, GPT-2-small (124.4 M params, vocab 50258), bf16 compute, N miners, ``local_steps`` optimizer steps per round
+followed by the fused delta all-gather -> weighted-average -> base broadcast (+ ``meta_steps`` learned-mixer steps).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 50 --warmup 5
+    python bench.py --impl reference ...      # the reference arm (see baseline/reference_arm.py)
+
+Two timed regions of exactly K steps each (both bracketed by barrier + cuda synchronize, CUDA events, max over ranks):
+  * ``value``: inputs already resident on the device (kernel/collective time only);
+  * ``e2e``:   through the public API (``training_manager.DeltaLoop.train``): every step copies its input batch from
+               pinned host memory and copies the step's loss back to pinned host memory.
+Every timed region performs at least one full averaging round.  Data: synthetic tokens; weights: random init.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--model", type=str, default="gpt2")
+    ap.add_argument("--batch-size", type=int, default=256, help="sequences per miner per step")
+    ap.add_argument("--seq-len", type=int, default=64, help="reference miner sequence length (neurons/miner.py:70)")
+    ap.add_argument("--local-steps", type=int, default=100)
+    ap.add_argument("--meta-steps", type=int, default=1, help="learned-mixer SGD steps per round on the averager rank")
+    ap.add_argument("--delta-dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp8"])
+    ap.add_argument("--lr", type=float, default=5e-4)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args(argv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def maybe_respawn(args) -> None:
+    """``python bench.py --gpus N`` without torchrun: re-launch ourselves under torch.distributed.run."""
+    if args.gpus > 1 and "RANK" not in os.environ:
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args) -> dict:
+    import torch
+    import torch.distributed as dist
+
+    from distributedtraining_b200 import ops
+    from distributedtraining_b200.data import SyntheticTokens
+    from distributedtraining_b200.models.trainer import Trainer
+    from distributedtraining_b200.parallel.exchange import CollectiveExchange, PeerExchange
+    from distributedtraining_b200.parallel.launch import barrier_sync, init_distributed, max_over_ranks
+    from distributedtraining_b200.parallel.local_sgd import LocalSGDCoordinator
+    from distributedtraining_b200.training_manager import DeltaLoop
+
+    rank, world, device = init_distributed("nccl")
+    assert device.type == "cuda", "bench.py needs a GPU"
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    B, T, K, W = args.batch_size, args.seq_len, args.steps, args.warmup
+    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0)  # same theta_base on every rank
+    V = trainer.cfg.vocab_size
+    if args.impl == "nccl":
+        ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
+        plane = "nccl all_gather + torch weighted sum" if world > 1 else "local torch"
+    else:
+        ex = PeerExchange(trainer.man, delta_dtype=args.delta_dtype)
+        plane = "peer windows (fused gather-avg-broadcast kernel)"
+    dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
+    host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
+    val = SyntheticTokens(B, T, V, seed=7, device=str(device), pool=2)
+    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps if args.impl != "nccl" else 0,
+                                val_batches=[b["input_ids"] for b in val.pool], post_pull_lr=5e-5)
+    # the optimizer keeps lr=5e-4 in round 0 and 5e-5 after the first pull, as in the reference miner
+
+    def run_steps(n: int, pool, gstep0: int, force_round: bool) -> int:
+        g = gstep0
+        did_round = False
+        for i in range(n):
+            trainer.step(pool[i % len(pool)]["input_ids"])
+            g += 1
+            if g % args.local_steps == 0:
+                coord.finish_round()
+                did_round = True
+        if force_round and not did_round:
+            coord.finish_round()
+        return g
+
+    # ---- warm-up (includes graph capture and one averaging round) ----
+    g = run_steps(max(W, 3), dev_data.pool, 0, force_round=True)
+    barrier_sync(device)
+
+    # ---- region 1: device-resident inputs ----
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    c0 = ops.launch_count()
+    rounds0 = coord.round
+    barrier_sync(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g = run_steps(K, dev_data.pool, 0, force_round=True)
+    e1.record()
+    barrier_sync(device)
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), device)
+    rounds = coord.round - rounds0
+    eager_launches = ops.launch_count() - c0
+    launches = K * trainer.launches_per_step + (eager_launches if trainer.use_graph else eager_launches - K * trainer.launches_per_step)
+    tokens = K * B * T * world
+    result = {
+        "metric": "tokens/sec (GPT-2-small local-SGD training, all miners; per-miner = value / n_gpus)",
+        "value": tokens / ms_total * 1e3, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic tokens (Zipf ids, right-padded), random-init weights", "impl": args.impl,
+        "tokens_per_s_per_miner": tokens / ms_total * 1e3 / world, "rounds_in_timed_region": rounds,
+        "avg_round_ms": ms_total / max(rounds, 1),
+        "config": {"model": f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})", "global_batch": B * world,
+                   "micro_batch_per_miner": B, "seq_len": T, "parallelism": f"local-sgd dp{world}", "local_steps": args.local_steps,
+                   "meta_steps_per_round": coord.meta_steps, "delta_dtype": args.delta_dtype, "exchange": plane,
+                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "cuda_graph": bool(trainer.use_graph),
+                   "l2_policy": "per-step working set (weights 0.25 GB bf16 + 1.5 GB fp32 state + ~5 GB activations) >> 126 MB L2"},
+        "clocks": clocks, "gpu_launches": int(launches),
+    }
+    # ---- region 2: end to end through the public API (pinned-host inputs, per-step loss read-back) ----
+    if not args.no_e2e:
+        loop = DeltaLoop(device, args.model, host_data, learning_rate=args.lr, hf_manager=None, trainer=trainer,
+                         local_steps=args.local_steps, round_hook=coord, max_steps=K, host_loss_every_step=True)
+        loop.global_step = 0
+        barrier_sync(device)
+        r0 = coord.round
+        e0.record()
+        loop.train(1)
+        if coord.round == r0:
+            coord.finish_round()
+        e1.record()
+        barrier_sync(device)
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1), device)
+        result["e2e"] = {"value": tokens / ms_e2e * 1e3, "unit": "tokens/s", "ms_per_step": ms_e2e / K,
+                         "h2d_bytes_per_step": B * T * 4, "d2h_bytes_per_step": 4, "api": "training_manager.DeltaLoop.train",
+                         "last_loss": float(loop.host_losses[-1]) if loop.host_losses is not None else None}
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return result if rank == 0 else {}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        from baseline.reference_arm import run_reference
+        out = run_reference(args)
+        if out:
+            print(json.dumps(out), flush=True)
+        return
+    maybe_respawn(args)
+    out = run_ours(args)
+    if out:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -170,9 +170,12 @@ class ParameterizedAverager(DeltaAverager):
 
     def __init__(self, model, device=None, hf_manager=None, local_dir: str = ".", gradients_dir: Optional[str] = None,
                  chain_manager=None, bittensor_network=None, hf_token=None, metrics: Optional[MetricsLogger] = None,
-                 cache_to_disk: bool = False, exchange=None):
+                 cache_to_disk: bool = False, exchange=None, fresh_only: bool = False, idle_timeout: float = 600.0):
         super().__init__(model, local_dir, bittensor_network, chain_manager, hf_manager, hf_token, device, gradients_dir, metrics)
         self.cache_to_disk = cache_to_disk
+        self.fresh_only = fresh_only  # only average deltas published since the last averaging (reference: re-averages stale ones)
+        self.idle_timeout = idle_timeout
+        self._consumed: Dict[str, int] = {}
         self.exchange = exchange if exchange is not None else getattr(hf_manager, "exchange", None)
         self.weights: Optional[torch.Tensor] = None  # w[N, P]
         self.deltas: List[torch.Tensor] = []         # resident flat deltas of the miners that delivered
@@ -203,9 +206,17 @@ class ParameterizedAverager(DeltaAverager):
         a miner without a repo / with a stale flag / with NaNs is skipped instead of crashing the round."""
         self.deltas, self.miner_hotkeys = [], []
         for hotkey, repo in self.get_model_paths():
+            if repo is None:
+                continue
+            if self.fresh_only and self.hf_manager is not None:
+                r = self.hf_manager.delta_round(repo)
+                if r <= self._consumed.get(hotkey, 0):
+                    continue
             flat = self.receive_gradients(repo)
             if flat is None:
                 continue
+            if self.fresh_only:
+                self._consumed[hotkey] = r
             flat = flat if flat.device == self.model.master.device else flat.to(self.model.master.device)
             self.deltas.append(flat)
             self.miner_hotkeys.append(hotkey)
@@ -292,12 +303,23 @@ class ParameterizedAverager(DeltaAverager):
             n = self.cache_params_locally()
             if n > 0:
                 self.weights = None  # N (and w) are rebuilt from scratch each round (reference :492)
-                self.meta_learning(val_loader, meta_epochs, lr)
+                if meta_epochs > 0:
+                    self.meta_learning(val_loader, meta_epochs, lr)
+                else:
+                    self.get_averaged_model()  # uniform mixer: w = 1/N, no meta-steps
                 self.save_model()
                 self._adopt_as_base()
                 self.push_to_hf_hub(commit_message="Updated model with new gradients")
+                idle_since = time.time()
             else:
-                logger.info("No valid deltas this round")
+                logger.debug("No valid deltas this round")
+                if self.fresh_only:  # wait for fresh submissions instead of burning a round
+                    idle_since = locals().get("idle_since", t0)
+                    if time.time() - idle_since > self.idle_timeout:
+                        logger.warning("averager idle timeout")
+                        return
+                    time.sleep(0.05)
+                    continue
             rounds += 1
             if max_rounds is not None and rounds >= max_rounds:
                 return

@@ -101,6 +101,13 @@ class HFManager:
             logger.warning(f"Error receiving delta from {miner_repo_id}: {e}")
             return None
 
+    def delta_round(self, miner_repo_id) -> int:
+        src = parse_repo(miner_repo_id)
+        try:
+            return 0 if src is None else int(self.exchange.delta_round(src))
+        except Exception:
+            return 0
+
     def receive_gradients(self, miner_repo_id, weights_file_name: str = "weight_diff.pt") -> Optional[Dict[str, torch.Tensor]]:
         """``dict[name -> Tensor]`` *views* of the miner's delta, or ``None`` (same contract as hf_manager.py:186-197)."""
         flat = self.receive_flat(miner_repo_id)

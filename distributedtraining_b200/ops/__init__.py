@@ -235,6 +235,7 @@ def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None)
     state.host_step += 1
     if not use_kernels(master):
         h = state.host
+        state.step += 1
         ref.adamw_step(master, p16, grad, m, v, lr=h["lr"], beta1=h["beta1"], beta2=h["beta2"], eps=h["eps"],
                        weight_decay=h["weight_decay"], step=state.host_step, grad_scale=h["grad_scale"])
         if delta is not None:

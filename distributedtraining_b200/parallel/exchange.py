@@ -41,6 +41,10 @@ class Exchange:
         """fp32-decodable flat delta of miner ``src`` for ``round`` or ``None`` if it has not been published."""
         raise NotImplementedError
 
+    def delta_round(self, src: int) -> int:
+        """Last round published by miner ``src`` (0 = nothing yet)."""
+        raise NotImplementedError
+
     def publish_base(self, base: torch.Tensor, round: int) -> None:
         raise NotImplementedError
 
@@ -80,6 +84,9 @@ class DiskExchange(Exchange):
                         device=trainer.master.device)
         trainer.emit_delta(d)
         self._atomic_save({"round": round, "fingerprint": self.man.fingerprint(), "delta": d.cpu()}, self._delta_path(self.rank))
+        with open(self._delta_path(self.rank) + ".round.tmp", "w") as f:
+            f.write(str(round))
+        os.replace(self._delta_path(self.rank) + ".round.tmp", self._delta_path(self.rank) + ".round")
 
     def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
         p = self._delta_path(src)
@@ -95,18 +102,25 @@ class DiskExchange(Exchange):
             return None
         return blob["delta"]
 
+    def delta_round(self, src: int) -> int:
+        p = self._delta_path(src) + ".round"
+        try:
+            return int(open(p).read().strip())
+        except Exception:
+            return 0
+
     def publish_base(self, base: torch.Tensor, round: int) -> None:
         self._atomic_save({"round": round, "fingerprint": self.man.fingerprint(), "base": base.detach().float().cpu()},
                           self._base_path())
+        with open(self._base_path() + ".round.tmp", "w") as f:
+            f.write(str(round))
+        os.replace(self._base_path() + ".round.tmp", self._base_path() + ".round")
 
     def base_round(self) -> int:
-        p = self._base_path()
-        if not os.path.exists(p):
-            return -1
         try:
-            return int(torch.load(p, map_location="cpu", weights_only=False)["round"])
+            return int(open(self._base_path() + ".round").read().strip())
         except Exception:
-            return -1
+            return 0
 
     def base_hash(self) -> Optional[str]:
         p = self._base_path()
@@ -193,6 +207,7 @@ class PeerExchange(Exchange):
             regions.update({"scale0": n // 32 * 4, "scale1": n // 32 * 4})
         if with_base16:
             regions["base16"] = n * 2
+        regions["w"] = 64 * len(manifest) * 4  # mixing matrix w[N<=64, P] shared by the averager
         self.win = SymmetricWindow(regions, group)
         self.rank, self.world = self.win.rank, self.win.world
         self.F_DELTA, self.F_BASE = F_DELTA, F_BASE
@@ -215,6 +230,9 @@ class PeerExchange(Exchange):
         """Delta is written straight into this rank's window (no copies), then the round flag is release-stored."""
         trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round))
         self.win.publish(self.F_DELTA, round, dst_ranks)
+
+    def delta_round(self, src: int) -> int:
+        return int(self.win.flags()[self.F_DELTA + src].item())
 
     def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
         flags = self.win.flags()

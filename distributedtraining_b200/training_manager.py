@@ -65,7 +65,8 @@ class TrainingLoop:
                  check_update_interval: float = 300, send_interval: float = 300, hf_manager=None, *, trainer=None,
                  batch_size: int = 1, seq_len: int = 64, local_steps: Optional[int] = 100, post_pull_lr: float = 5e-5,
                  reset_optimizer: bool = True, max_steps: Optional[int] = None, metrics: Optional[MetricsLogger] = None,
-                 round_hook: Optional[Callable] = None, seed: int = 0, my_hotkey: str = "miner"):
+                 round_hook: Optional[Callable] = None, seed: int = 0, my_hotkey: str = "miner",
+                 host_loss_every_step: bool = False):
         self.device = device
         self.model_name = model_name
         # the reference loads tokenizer + AutoModelForCausalLM.from_pretrained here (:39-46); offline we build the
@@ -90,6 +91,14 @@ class TrainingLoop:
         self.my_hotkey = my_hotkey
         self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.model.master.device)
         self._loss_n = 0
+        # optional per-step device->host read-back of the loss into pinned memory (asynchronous; the reference blocks on
+        # loss.item() every step, training_manager.py:388)
+        self.host_losses = None
+        if host_loss_every_step:
+            n = max_steps or 1024
+            self.host_losses = torch.zeros(n, dtype=torch.float32)
+            if torch.cuda.is_available():
+                self.host_losses = self.host_losses.pin_memory()
         if MLFLOW_ACTIVE:
             initialize_mlflow(role="miner", device=device, version=None, my_hotkey=my_hotkey, learning_rate=learning_rate,
                               send_interval=send_interval, check_update_interval=check_update_interval)
@@ -186,6 +195,8 @@ class DeltaLoop(TrainingLoop):
                 if self._due_poll():
                     self._maybe_pull()
                 loss = m.step(_ids_of(batch), _labels_of(batch))
+                if self.host_losses is not None:
+                    self.host_losses[self.global_step % self.host_losses.numel()].copy_(loss, non_blocking=True)
                 self._loss_acc += loss
                 self._loss_n += 1
                 self.global_step += 1

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Averager neuron (reference neurons/averager.py): gather every miner's delta, learn the per-(miner, tensor) mixing
+weights on validation data, publish the weighted average as the next base model."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from distributedtraining_b200.averaging_logic import DeltaAverager, GeneticAverager, ParameterizedAverager  # noqa: E402
+from distributedtraining_b200.data import SyntheticTokens  # noqa: E402
+from distributedtraining_b200.models.trainer import Trainer  # noqa: E402
+from distributedtraining_b200.runtime import build_context  # noqa: E402
+
+EVAL_SEQ = 512     # reference neurons/averager.py:72
+EVAL_TEXTS = 100   # :61
+PERIOD = 1200      # :106
+
+
+def main(argv=None):
+    ctx = build_context("averager", argv)
+    cfg = ctx.config
+    bs = cfg.batch_size
+    seq = min(EVAL_SEQ, cfg.seq_len * 8) if cfg.model.endswith("tiny") else EVAL_SEQ
+    trainer = Trainer(cfg.model, device=ctx.device, batch=bs, seq=seq, lr=cfg.lr, seed=0, use_graph=False)
+    n_batches = (EVAL_TEXTS + bs - 1) // bs if not cfg.rounds else max(1, min(4, EVAL_TEXTS // bs))
+    val_loader = list(SyntheticTokens(bs, seq, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1, seed=4242,
+                                      steps=n_batches, pool=n_batches))
+    kw = dict(hf_manager=ctx.hf_manager, local_dir=cfg.storage.model_dir, gradients_dir=cfg.storage.gradient_dir,
+              chain_manager=ctx.chain, bittensor_network=ctx.network, metrics=ctx.metrics, fresh_only=bool(cfg.rounds))
+    period = 0 if cfg.rounds else PERIOD
+    if cfg.mixer == "genetic":
+        avg = GeneticAverager(trainer, ctx.device, **kw)
+        for _ in range(cfg.rounds or 1 << 62):
+            if avg.cache_params_locally():
+                avg.run_evolution(val_loader)
+                avg.save_model(); avg._adopt_as_base(); avg.push_to_hf_hub()
+    elif cfg.mixer in ("uniform", "score"):
+        avg = ParameterizedAverager(trainer, ctx.device, **kw)
+        avg.run_periodic_averaging(val_loader, 0, cfg.meta_lr, period, max_rounds=cfg.rounds or None)
+    else:
+        avg = ParameterizedAverager(trainer, ctx.device, **kw)
+        # reference: run_periodic_averaging(test_loader, 7, 0.01, 1200)  (neurons/averager.py:106)
+        avg.run_periodic_averaging(val_loader, cfg.meta_epochs, cfg.meta_lr, period, max_rounds=cfg.rounds or None)
+    return avg
+
+
+if __name__ == "__main__":
+    main()

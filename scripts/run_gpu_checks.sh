@@ -1,3 +1,4 @@
-timeout 300 python -m pytest tests/test_attention_gpu.py -x -q 2>&1 | tail -15
-timeout 300 python -m pytest tests/test_ops_gpu.py tests/test_engine.py -m gpu -x -q 2>&1 | tail -5
-for b in 256; do timeout 300 python scripts/step_bench.py --batch $b 2>&1 | tail -2; done
+set -x
+timeout 600 python bench.py --gpus 1 --steps 40 --warmup 5 2>&1 | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29501 scripts/peer_check.py 2>&1 | tail -8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29502 bench.py --gpus 2 --steps 40 --warmup 5 2>&1 | tail -4

@@ -1,0 +1,40 @@
+"""Multi-GPU tests (need >= 2 devices; launched through torchrun, NCCL control plane, peer-memory data plane)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_peer_exchange_matches_nccl_reference():
+    n = min(_ngpu(), 4)
+    env = dict(os.environ, PEER_CHECK_MB="8")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "scripts", "peer_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("PEER_CHECK ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(line[-1][len("PEER_CHECK "):])
+    assert out["all_ranks_ok"], out
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_bench_two_gpus_runs():
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29612", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "6",
+                        "--warmup", "3", "--model", "gpt2-tiny", "--batch-size", "8", "--local-steps", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(lines[-1])
+    assert out["n_gpus"] == 2 and out["value"] > 0 and out["rounds_in_timed_region"] >= 2 and out["e2e"]["value"] > 0
