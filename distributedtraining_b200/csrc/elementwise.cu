@@ -44,7 +44,8 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // embedding
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
-                                 bf16* __restrict__ out, int M, int T, int d) {
+                                 bf16* __restrict__ out, int M, int T, int d, const bf16* __restrict__ wte2,
+                                 const bf16* __restrict__ wpe2) {
   const int row = blockIdx.x;
   const int id = ids[row];
   const int pos = row % T;
@@ -58,6 +59,16 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __rest
       unpack8(__ldg(p + i), b);
 #pragma unroll
       for (int k = 0; k < 8; ++k) a[k] += b[k];
+    }
+    if (wte2) {  // second table (e.g. a miner's delta living in a peer window): rows are added on the fly
+      unpack8(__ldg(reinterpret_cast<const uint4*>(wte2 + size_t(id) * d) + i), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += b[k];
+      if (wpe2) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(wpe2 + size_t(pos) * d) + i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += b[k];
+      }
     }
     o[i] = pack8(a);
   }
@@ -450,8 +461,10 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot
 using namespace dtb;
 #define KCHECK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
-extern "C" int dtb_embed_fwd(const int* ids, const void* wte, const void* wpe, void* out, int M, int T, int d, cudaStream_t s) {
-  embed_fwd_kernel<<<M, 128, 0, s>>>(ids, (const bf16*)wte, (const bf16*)wpe, (bf16*)out, M, T, d);
+extern "C" int dtb_embed_fwd(const int* ids, const void* wte, const void* wpe, void* out, int M, int T, int d, cudaStream_t s,
+                             const void* wte2, const void* wpe2) {
+  embed_fwd_kernel<<<M, 128, 0, s>>>(ids, (const bf16*)wte, (const bf16*)wpe, (bf16*)out, M, T, d, (const bf16*)wte2,
+                                     (const bf16*)wpe2);
   return KCHECK();
 }
 extern "C" int dtb_embed_bwd(const void* dx, const int* ids, float* dwte, float* dwpe, int M, int T, int d, cudaStream_t s) {

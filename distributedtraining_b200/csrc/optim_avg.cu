@@ -173,7 +173,9 @@ struct AvgParams {
   int* nan_flags;                      // [N], set to 1 if miner i's delta holds a non-finite value
   int* error_flag;                     // set to 1 on a flag-wait timeout
   int N, P, n_out, mode;               // mode: 0 fp32, 1 bf16, 2 fp8-block
-  int chunk_begin, chunk_end;          // shard of the chunk table processed by this launch
+  int chunk_begin, chunk_end;          // shard of the chunk table (or of chunk_ids) processed by this launch
+  const int32_t* chunk_ids;            // optional indirection: process chunk_ids[chunk_begin..chunk_end)
+  int unit_base;                       // 1: theta = base + sum_i w_i delta_i (delta APPLY), 0: s_j = sum_i w_ij (averaging)
   uint32_t wait_value;
 };
 
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
   }
   int bad = 0;  // bitmask (per thread) of miners with non-finite data; N <= 64 -> two 32-bit words
   int bad_hi = 0;
-  for (int c = p.chunk_begin + blockIdx.x; c < p.chunk_end; c += gridDim.x) {
+  for (int ci = p.chunk_begin + blockIdx.x; ci < p.chunk_end; ci += gridDim.x) {
+    const int c = p.chunk_ids ? p.chunk_ids[ci] : ci;
     const int j = p.chunk_tid[c];
     const size_t start = size_t(p.chunk_start[c]);
     const int len = p.chunk_len[c];
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int i = 0; i < p.N; ++i) s += s_w[i];
-      s_w[kMaxMiners] = s;
+      s_w[kMaxMiners] = p.unit_base ? 1.f : s;
     }
     __syncthreads();
     const float s_sum = s_w[kMaxMiners];
@@ -481,7 +484,8 @@ extern "C" int dtb_round_reset(const float* base, float* master, void* p16, floa
 extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const uint32_t** wait_flags, uint32_t wait_value,
                               const float* base, const float* w, const int64_t* chunk_start, const int32_t* chunk_len,
                               const int32_t* chunk_tid, int chunk_begin, int chunk_end, float** outs_f32, void** outs_bf16,
-                              int n_out, int* nan_flags, int* error_flag, int N, int P, int mode, int grid, cudaStream_t s) {
+                              int n_out, int* nan_flags, int* error_flag, int N, int P, int mode, int grid, cudaStream_t s,
+                              const int32_t* chunk_ids, int unit_base) {
   if (N > kMaxMiners || n_out > kMaxOut) return 3;
   AvgParams p{};
   for (int i = 0; i < N; ++i) {
@@ -496,6 +500,7 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
   p.base = base; p.w = w; p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.chunk_tid = chunk_tid;
   p.nan_flags = nan_flags; p.error_flag = error_flag; p.N = N; p.P = P; p.n_out = n_out; p.mode = mode;
   p.chunk_begin = chunk_begin; p.chunk_end = chunk_end; p.wait_value = wait_flags ? wait_value : 0;
+  p.chunk_ids = chunk_ids; p.unit_base = unit_base;
   if (grid > chunk_end - chunk_begin) grid = chunk_end - chunk_begin;
   if (grid < 1) return 0;
   if (mode == 0) gather_avg_kernel<0><<<grid, 256, 0, s>>>(p);

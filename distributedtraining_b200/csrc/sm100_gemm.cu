@@ -36,8 +36,8 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kSlabBytes = BLOCK_M * 128;       // 16 KB: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 constexpr int kNumSlabBufs = 2;
 constexpr int kTmemCols = 512;
-constexpr int kNumThreads = 192;                // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 352;                // warp0 TMA, warp1 MMA, warps2-9 epilogue (2 groups of 4), warp10 persist
+constexpr int kEpiThreads = 256;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNumSlabBufs * kSlabBytes + BLOCK_N * 4 /*bias*/ + 256 /*barriers*/;
 
 enum Epi : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_RESID = 3, EPI_DGELU = 4, EPI_RESID = 5 };
@@ -47,6 +47,10 @@ struct GemmParams {
   CUtensorMap tmap_b;
   CUtensorMap tmap_c;
   CUtensorMap tmap_c2;  // second output (pre-activation) for EPI_BIAS_GELU
+  CUtensorMap tmap_aux; // residual / pre-activation input tile for EPI_*RESID / EPI_DGELU
+  CUtensorMap tmap_b2;  // optional second B operand: C = A (B + B2)^T computed as two accumulating MMA passes
+  CUtensorMap tmap_bp;  // optional local destination: B tiles pulled from a peer are persisted here as a side effect
+  int dual_b, persist_b;
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, num_kb;
   int epi;
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* aux_bars = tmem_empty_bar + 2;  // [2] one per epilogue group
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bars + 2);
 
   const uint32_t warp_idx = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -101,13 +106,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
     tma_prefetch_desc(&p.tmap_c);
+    tma_prefetch_desc(&p.tmap_aux);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.persist_b ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kEpiThreads / 32);
+      mbar_init(&aux_bars[i], 1);
     }
     fence_barrier_init();
   }
@@ -133,25 +140,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem_ab + stage * kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
-          const int k0 = kb * BLOCK_K;
-          if constexpr (A_MN) {
+        const int kreps = p.dual_b ? 2 : 1;
+        for (int rep = 0; rep < kreps; ++rep) {
+          const CUtensorMap* bmap = rep == 0 ? &p.tmap_b : &p.tmap_b2;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem_ab + stage * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[stage], kStageBytes);
+            const int k0 = kb * BLOCK_K;
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
-          } else {
-            tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
-          }
-          if constexpr (B_MN) {
+              for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
+            } else {
+              tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
+            }
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), &p.tmap_b, &full_bar[stage], n0 + a * 64, k0);
-          } else {
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], k0, n0);
+              for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0);
+            } else {
+              tma_load_2d(sb, bmap, &full_bar[stage], k0, n0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -171,7 +182,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const int nk = (kb1 - kb0) * (p.dual_b ? 2 : 1);
+      for (int ki = 0; ki < nk; ++ki) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -181,60 +193,101 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          if (ki == nk - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (warp_idx == 10) {
+    // ===================== persist warp (fused broadcast -> GEMM) =====================
+    // When B is pulled from a PEER window, the CTA that owns the first M-tile of each N-tile TMA-stores every B stage
+    // to the local weight copy while the MMA consumes it: the broadcast rides on the first forward GEMM.
+    if (p.persist_b && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_t = w % p.tiles_n;
+        const int m_t = (w / p.tiles_n) % p.tiles_m;
+        const int sp = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int n0 = n_t * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (m_t == 0) {
+            const uint8_t* sb = smem_ab + stage * kStageBytes + kABytes;
+            const int k0 = kb * BLOCK_K;
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int a = 0; a < BLOCK_N / 64; ++a) tma_store_2d(&p.tmap_bp, sb + a * (BLOCK_K * 128), n0 + a * 64, k0);
+            } else {
+              tma_store_2d(&p.tmap_bp, sb, k0, n0);
+            }
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9): two independent groups of 4 warps =====================
+    // Group g handles slabs g, g+2, ... of every tile with its own staging buffer, named barrier, aux mbarrier and TMA
+    // issuer thread.  Two warps per SM sub-partition hide the ALU/MUFU latency of the fused epilogues; the aux tile
+    // (residual / pre-activation) is TMA-loaded INTO the staging buffer and transformed in place.
+    const uint32_t ewarp = warp_idx - 2;             // 0..7
+    const uint32_t grp = ewarp >> 2;                 // 0 / 1
     const uint32_t quad = warp_idx & 3;              // TMEM lane quadrant this warp may access
     const uint32_t row_l = quad * 32 + lane;         // row within the tile
-    const uint32_t epi_tid = threadIdx.x - 64;       // 0..127
-    const bool issuer = (epi_tid == 0);
-    uint32_t acc = 0, acc_phase = 0;
-    uint32_t slab_ctr = 0;
+    const uint32_t epi_tid = threadIdx.x - 64;       // 0..255
+    const bool issuer = (lane == 0) && ((ewarp & 3) == 0);  // one issuer thread per group
+    const uint32_t bar_id = 1 + grp;                 // named barriers 1 / 2 (group-local, 128 threads)
+    uint8_t* buf = smem_slab + grp * kSlabBytes;
+    uint64_t* aux_bar = tmem_empty_bar + 2 + grp;    // after tmem_empty[2]
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
     constexpr int kColsPerSlab = OUT_F32 ? 32 : 64;
     constexpr int kSlabs = BLOCK_N / kColsPerSlab;
+    const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
+    const bool has_aux = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
+    const bool dual = (p.epi == EPI_BIAS_GELU);
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int n_t = w % p.tiles_n;
       const int m_t = (w / p.tiles_n) % p.tiles_m;
       const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
-      const int row = m0 + row_l;
-      const bool row_ok = row < p.M;
-      const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
       if (has_bias) {
-        named_bar_sync(2, kEpiThreads);  // previous tile's readers of smem_bias are done
+        named_bar_sync(3, kEpiThreads);  // previous tile's readers of smem_bias are done
         for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) {
           int c = n0 + i;
           smem_bias[i] = (c < p.N) ? __bfloat162float(p.bias[c]) : 0.f;
         }
-        named_bar_sync(2, kEpiThreads);
+        named_bar_sync(3, kEpiThreads);
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + acc * BLOCK_N + ((quad * 32u) << 16);
 #pragma unroll 1
-      for (int s = 0; s < kSlabs; ++s) {
+      for (int s = grp; s < kSlabs; s += 2) {
         const int c0 = s * kColsPerSlab;  // column offset inside the tile
+        const int gcol0 = n0 + c0;
+        const bool last = (s + 2 >= kSlabs);
+        uint8_t* rowp = buf + row_l * 128;
         if constexpr (OUT_F32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr_row + c0, r);
           tmem_ld_wait();
-          if (s == kSlabs - 1) {  // accumulator fully drained -> hand TMEM stage back to the MMA warp
+          if (last) {  // this warp has drained its share of the accumulator -> hand the TMEM stage back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
-          uint8_t* buf = smem_slab + (slab_ctr & 1) * kSlabBytes;
-          if (issuer) tma_store_wait_read<1>();
-          named_bar_sync(1, kEpiThreads);
-          uint8_t* rowp = buf + row_l * 128;
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float4 v;
@@ -245,32 +298,35 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             *reinterpret_cast<float4*>(rowp + ((ch ^ (row_l & 7)) << 4)) = v;
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(bar_id, 128);
           if (issuer) {
-            if (n0 + c0 < p.N) tma_reduce_add_2d(&p.tmap_c, buf, n0 + c0, m0);
+            if (gcol0 < p.N) tma_reduce_add_2d(&p.tmap_c, buf, gcol0, m0);
             tma_store_commit();
           }
-          ++slab_ctr;
         } else {
+          if (has_aux) {  // aux slab -> staging buffer (async), overlapped with the TMEM read below
+            if (issuer) {
+              tma_store_wait_read<0>();
+              mbar_expect_tx(aux_bar, kSlabBytes);
+              tma_load_2d(buf, &p.tmap_aux, aux_bar, gcol0, m0);
+            }
+          }
           uint32_t r[64];
           tmem_ld_32x32b_x32(taddr_row + c0, r);
           tmem_ld_32x32b_x32(taddr_row + c0 + 32, r + 32);
           tmem_ld_wait();
-          if (s == kSlabs - 1) {
+          if (last) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
-          const bool dual = (p.epi == EPI_BIAS_GELU);
-          uint8_t* buf = smem_slab + (dual ? 0 : (slab_ctr & 1)) * kSlabBytes;
-          uint8_t* buf2 = smem_slab + kSlabBytes;
-          if (issuer) {
-            if (dual) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          if (has_aux) {
+            mbar_wait(aux_bar, aux_phase);
+            aux_phase ^= 1;
+          } else {
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, 128);
           }
-          named_bar_sync(1, kEpiThreads);
-          uint8_t* rowp = buf + row_l * 128;
-          uint8_t* rowp2 = buf2 + row_l * 128;
-          const int gcol0 = n0 + c0;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float v[8];
@@ -282,20 +338,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            if (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU) {
+            const uint32_t sw = ((ch ^ (row_l & 7)) << 4);
+            if (has_aux) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rowp + sw);
               float a[8];
-              const int gc = gcol0 + ch * 8;
-              if (row_ok && gc < p.N) {
-                const uint4 q = *reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + gc);
-                float2 f;
-                f = unpack_bf16x2(q.x); a[0] = f.x; a[1] = f.y;
-                f = unpack_bf16x2(q.y); a[2] = f.x; a[3] = f.y;
-                f = unpack_bf16x2(q.z); a[4] = f.x; a[5] = f.y;
-                f = unpack_bf16x2(q.w); a[6] = f.x; a[7] = f.y;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = 0.f;
-              }
+              float2 f;
+              f = unpack_bf16x2(q.x); a[0] = f.x; a[1] = f.y;
+              f = unpack_bf16x2(q.y); a[2] = f.x; a[3] = f.y;
+              f = unpack_bf16x2(q.z); a[4] = f.x; a[5] = f.y;
+              f = unpack_bf16x2(q.w); a[6] = f.x; a[7] = f.y;
               if (p.epi == EPI_DGELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= dgelu_tanh_f(a[i]);
@@ -304,30 +355,39 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
                 for (int i = 0; i < 8; ++i) v[i] += a[i];
               }
             }
-            const uint32_t sw = ((ch ^ (row_l & 7)) << 4);
-            if (dual) {
-              uint4 o2;
-              o2.x = pack_bf16x2(v[0], v[1]); o2.y = pack_bf16x2(v[2], v[3]);
-              o2.z = pack_bf16x2(v[4], v[5]); o2.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(rowp2 + sw) = o2;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_f(v[i]);
-            }
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
             *reinterpret_cast<uint4*>(rowp + sw) = o;
+            if (dual) {  // keep gelu(u) in registers (re-packed into r) for the second store
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_f(v[i]);
+              r[ch * 4 + 0] = pack_bf16x2(v[0], v[1]); r[ch * 4 + 1] = pack_bf16x2(v[2], v[3]);
+              r[ch * 4 + 2] = pack_bf16x2(v[4], v[5]); r[ch * 4 + 3] = pack_bf16x2(v[6], v[7]);
+            }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(bar_id, 128);
           if (issuer) {
-            if (gcol0 < p.N) {
-              tma_store_2d(&p.tmap_c, buf, gcol0, m0);
-              if (dual) tma_store_2d(&p.tmap_c2, buf2, gcol0, m0);
-            }
+            if (gcol0 < p.N) tma_store_2d(dual ? &p.tmap_c2 : &p.tmap_c, buf, gcol0, m0);
             tma_store_commit();
           }
-          ++slab_ctr;
+          if (dual) {  // second output: gelu(pre-activation) through the same buffer
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              uint4 o;
+              o.x = r[ch * 4 + 0]; o.y = r[ch * 4 + 1]; o.z = r[ch * 4 + 2]; o.w = r[ch * 4 + 3];
+              *reinterpret_cast<uint4*>(rowp + ((ch ^ (row_l & 7)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (issuer) {
+              if (gcol0 < p.N) tma_store_2d(&p.tmap_c, buf, gcol0, m0);
+              tma_store_commit();
+            }
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -396,7 +456,8 @@ static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
 // out_f32 => C is fp32 and the tile is reduce-ADDED into it (caller zeroes C); splits > 1 requires out_f32.
 extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                              int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
-                             float alpha, int splits, int num_sms, cudaStream_t stream) {
+                             float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,
+                             void* b_persist, int ldbp) {
   using namespace dtb;
   GemmParams p;
   int rc = 0;
@@ -408,6 +469,21 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   else         rc |= make_tmap_2d(&p.tmap_c, c, 2, N, M, ldc, 64, BLOCK_M);
   if (c2) rc |= make_tmap_2d(&p.tmap_c2, c2, 2, N, M, ldc2, 64, BLOCK_M);
   else    p.tmap_c2 = p.tmap_c;
+  if (aux) rc |= make_tmap_2d(&p.tmap_aux, aux, 2, N, M, ldaux, 64, BLOCK_M);
+  else     p.tmap_aux = p.tmap_c;
+  p.dual_b = b2 != nullptr;
+  p.persist_b = b_persist != nullptr;
+  p.tmap_b2 = p.tmap_b;
+  p.tmap_bp = p.tmap_b;
+  if (b2) {
+    if (b_mn) rc |= make_tmap_2d(&p.tmap_b2, b2, 2, N, K, ldb2, 64, BLOCK_K);
+    else      rc |= make_tmap_2d(&p.tmap_b2, b2, 2, K, N, ldb2, BLOCK_K, BLOCK_N);
+  }
+  if (b_persist) {
+    if (b_mn) rc |= make_tmap_2d(&p.tmap_bp, b_persist, 2, N, K, ldbp, 64, BLOCK_K);
+    else      rc |= make_tmap_2d(&p.tmap_bp, b_persist, 2, K, N, ldbp, BLOCK_K, BLOCK_N);
+  }
+  if (p.dual_b && p.persist_b) return 2001;  // one or the other
   if (rc) return 1000 + rc;
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;

@@ -256,6 +256,9 @@ class TransformerEngine:
         self.dev = params.device
         self.cdtype = params.dtype
         self.P = ModelParams(cfg, manifest, params)
+        self.P_flat = params
+        self._delta = self._src = None
+        self._src_flat = None
         self.G = ModelParams(cfg, manifest, grads) if grads is not None else None
         self.grads = grads
         d, Fd, M = cfg.n_embd, cfg.ffn_dim, self.M
@@ -324,27 +327,65 @@ class TransformerEngine:
         self.targets[:n, :-1].copy_(src[:, 1:], non_blocking=True)
 
     # -- forward ---------------------------------------------------------------------------------------------------
+    def set_delta(self, delta_flat: Optional[torch.Tensor]) -> None:
+        """Fused delta evaluation (validator): every weight GEMM computes ``x (W + dW)^T`` as two accumulating tensor-core
+        passes with ``dW`` read straight from ``delta_flat`` (bf16, may live in a miner's PEER window) and the embedding
+        adds the delta rows on the fly -- ``theta_base + delta_i`` is never materialised for the matrices.  The small
+        tensors (norm weights, biases) must already hold base+delta in the compute arena (see ``small_chunk_ids``)."""
+        self._delta = None if delta_flat is None else ModelParams(self.cfg, self.man, delta_flat)
+
+    def set_source(self, src_flat: Optional[torch.Tensor]) -> None:
+        """Fused broadcast -> first forward: weights are read from ``src_flat`` (the averager's bf16 window over NVLink)
+        and every B tile is persisted into this rank's compute arena by the GEMM that consumes it."""
+        self._src = None if src_flat is None else ModelParams(self.cfg, self.man, src_flat)
+        self._src_flat = src_flat
+
+    def small_chunk_ids(self) -> torch.Tensor:
+        """Chunk-table indices of the non-matrix tensors (norm weights, biases, positional table)."""
+        if getattr(self, "_small_ids", None) is None:
+            _, _, ct = self.man.seg_table(self.dev)
+            small = torch.tensor([len(s.shape) < 2 or s.name.endswith("wpe.weight") for s in self.man.specs], device=self.dev)
+            self._small_ids = torch.nonzero(small[ct.long()]).flatten().to(torch.int32)
+        return self._small_ids
+
+    def _w(self, l: Optional[int], name: str) -> dict:
+        """kwargs (b, b2, b_persist) of the weight operand ``name`` of layer ``l`` (None = model level)."""
+        pick = (lambda P: getattr(P.layers[l], name)) if l is not None else (lambda P: getattr(P, name))
+        delta, src = getattr(self, "_delta", None), getattr(self, "_src", None)
+        if src is not None:
+            return {"b": pick(src), "b_persist": pick(self.P)}
+        if delta is not None:
+            return {"b": pick(self.P), "b2": pick(delta)}
+        return {"b": pick(self.P)}
+
     def forward(self, train: bool = True) -> None:
-        cfg, P = self.cfg, self.P
+        cfg = self.cfg
+        delta, src = getattr(self, "_delta", None), getattr(self, "_src", None)
+        P = src if src is not None else self.P  # small tensors (norms, biases, embeddings) are read where the weights are
         B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
-        ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0])
+        # the position table belongs to the small set (already base+delta in the arena): only the token rows are added here
+        ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0], *((delta.wte, None) if delta is not None else ()))
         for l, Lp in enumerate(P.layers):
             x = self.xs[l]
             self._norm_fwd(x, Lp.ln1_w, Lp.ln1_b, self.h1[l], self.mean1[l], self.rstd1[l])
-            ops.gemm(self.h1[l], Lp.qkv_w, self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b)
+            g = self._w(l, "qkv_w")
+            ops.gemm(self.h1[l], g.pop("b"), self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b, **g)
             if cfg.family == "llama":
                 ops.rope_(self.qkv[l], B, T, H, Hkv, hd, cfg.rope_theta)
             ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv)
-            ops.gemm(self.att[l], Lp.o_w, self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
-                     aux=x)
+            g = self._w(l, "o_w")
+            ops.gemm(self.att[l], g.pop("b"), self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
+                     aux=x, **g)
             self._norm_fwd(self.xmid[l], Lp.ln2_w, Lp.ln2_b, self.h2[l], self.mean2[l], self.rstd2[l])
+            g = self._w(l, "fc_w")
             if cfg.family == "gpt2":
-                ops.gemm(self.h2[l], Lp.fc_w, self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l])
+                ops.gemm(self.h2[l], g.pop("b"), self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l], **g)
             else:
-                ops.gemm(self.h2[l], Lp.fc_w, self.u[l])
+                ops.gemm(self.h2[l], g.pop("b"), self.u[l], **g)
                 ops.swiglu_fwd(self.u[l], self.act[l])
-            ops.gemm(self.act[l], Lp.proj_w, self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
-                     bias=Lp.proj_b, aux=self.xmid[l])
+            g = self._w(l, "proj_w")
+            ops.gemm(self.act[l], g.pop("b"), self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
+                     bias=Lp.proj_b, aux=self.xmid[l], **g)
         self._norm_fwd(self.xs[-1], P.lnf_w, P.lnf_b, self.xf, self.meanf, self.rstdf)
 
     def _lm_head(self, backward: bool) -> None:
@@ -353,17 +394,33 @@ class TransformerEngine:
         n_valid = self.n_rows * (self.T - 1)
         scale = 1.0 / max(n_valid, 1)
         tgt = self.targets.view(-1)
+        first = True
         for c0 in range(0, self.M, self.lm_chunk):
             c1 = min(self.M, c0 + self.lm_chunk)
             lg = self.logits[:c1 - c0]  # [rows, ldl] padded pitch; lgv is the logical [rows, V] view (TMA clips/zero-fills)
             lgv = lg[:, :V]
-            ops.gemm(self.xf[c0:c1], P.wte, lgv)
+            g = self._w(None, "wte")
+            if not first:
+                g.pop("b_persist", None)  # the first chunk's GEMM already persisted the table
+                if getattr(self, "_src", None) is not None:
+                    g["b"] = P.wte
+            ops.gemm(self.xf[c0:c1], g.pop("b"), lgv, **g)
+            first = False
             ops.ce_fwd_bwd(lg, tgt[c0:c1], V, self.losses[c0:c1], scale if backward else None)
             if backward:
                 ops.gemm(lgv, P.wte, self.dxf[c0:c1], b_mn=True)  # dxf = dlogits @ wte
                 ops.gemm(lgv, self.xf[c0:c1], self.G.wte, a_mn=True, b_mn=True, accumulate=True)  # dwte += dlogits^T xf
         torch.sum(self.losses, dim=0, out=self.loss)
         self.loss.mul_(scale)
+
+    def persist_small_from_source(self) -> None:
+        """Copy the non-matrix tensors (norms, biases, position table: < 1 % of the bytes) from the peer source."""
+        src = getattr(self, "_src", None)
+        if src is None:
+            return
+        for s in self.man.specs:
+            if len(s.shape) < 2 or s.name.endswith("wpe.weight"):
+                self.man.view(self.P_flat, s.name).copy_(self.man.view(self._src_flat, s.name), non_blocking=True)
 
     def forward_loss(self) -> torch.Tensor:
         """Eval forward: mean next-token CE over the batch in the static buffers (device scalar)."""

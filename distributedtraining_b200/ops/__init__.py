@@ -44,15 +44,20 @@ def _row_major(t: torch.Tensor, what: str) -> int:
 # GEMM
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=0):
+         splits=0, b2=None, b_persist=None):
     """out[M,N] = epi(alpha * A @ B^T) -- see :func:`reference.gemm` for the operand conventions.
 
     CUDA: persistent tcgen05/TMEM/TMA kernel (csrc/sm100_gemm.cu).  fp32 ``out`` is always reduce-ADDED by TMA
     (split-K capable); pass ``accumulate=False`` to have it zeroed first.
+
+    ``b2``: second B operand of the same shape -- computes ``A (B + B2)^T`` as two accumulating tensor-core passes (the
+    validator's ``theta_base + delta_i`` eval without materialising the sum; B2 may live in a peer window).
+    ``b_persist``: local destination of the same shape as ``b`` -- when ``b`` is read from a PEER window (fused
+    broadcast -> first forward GEMM) every B tile is also TMA-stored there while the MMA consumes it.
     """
     if not use_kernels(out):
         return ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
-                        accumulate=accumulate)
+                        accumulate=accumulate, b2=b2, b_persist=b_persist)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb, ldc = _row_major(a, "a"), _row_major(b, "b"), _row_major(out, "out")
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -76,7 +81,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     rc = _lib.lib().dtb_gemm_bf16(
         _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), int(out_f32), EPI[epi],
         _lib.ptr(bias), _lib.ptr(aux), ldaux, _lib.ptr(out2), ldc2, ctypes.c_float(alpha), splits, _lib.num_sms(),
-        _lib.stream_ptr())
+        _lib.stream_ptr(), _lib.ptr(b2), _row_major(b2, "b2") if b2 is not None else 0, _lib.ptr(b_persist),
+        _row_major(b_persist, "b_persist") if b_persist is not None else 0)
     _c(rc, "gemm")
     _tick()
     return out
@@ -85,12 +91,18 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
 # ---------------------------------------------------------------------------------------------------------------------
 # embedding / norms / activations / loss
 # ---------------------------------------------------------------------------------------------------------------------
-def embed_fwd(ids, wte, wpe, out):
+def embed_fwd(ids, wte, wpe, out, wte2=None, wpe2=None):
+    """out = wte[ids] + wpe[pos] (+ wte2[ids] + wpe2[pos]: a second table, e.g. a delta in a peer window)."""
     if not use_kernels(out):
-        return ref.embed_fwd(ids.long(), wte, wpe, out)
+        ref.embed_fwd(ids.long(), wte, wpe, out)
+        if wte2 is not None:
+            tmp = torch.empty_like(out)
+            ref.embed_fwd(ids.long(), wte2, wpe2, tmp)
+            out.add_(tmp)
+        return out
     M, d = out.shape
     _c(_lib.lib().dtb_embed_fwd(_lib.ptr(ids), _lib.ptr(wte), _lib.ptr(wpe), _lib.ptr(out), M, ids.shape[-1], d,
-                                _lib.stream_ptr()), "embed_fwd")
+                                _lib.stream_ptr(), _lib.ptr(wte2), _lib.ptr(wpe2)), "embed_fwd")
     _tick()
     return out
 
@@ -322,7 +334,7 @@ def _dp(t) -> int:
 
 
 def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales=None, nan_flags=None, wait_flags=None,
-                 wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None):
+                 wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None, chunk_ids=None, unit_base=False):
     """Fused kernel (a): ``theta_new = s_j*base + sum_i w[i,j]*delta_i`` written to every destination in ``outs_*``.
 
     ``deltas`` / ``outs_*`` entries are tensors or raw (peer-mapped) device addresses.  ``chunk_range`` restricts the
@@ -340,15 +352,26 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
             dl = [dequant_fp8(d, s) for d, s in zip(deltas, dscales)]
         tmp = torch.empty_like(base, dtype=torch.float32)
         ref.weighted_avg(base, dl, w, tid, tmp, nan_flags)
-        for o in outs_f32:
+        if unit_base:
+            tmp.add_(base * (1.0 - w.sum(0)[tid]))
+        sel = None
+        if chunk_ids is not None or chunk_range is not None:
+            cs, cl, _ = manifest.seg_table(base.device)
+            ids = chunk_ids if chunk_ids is not None else torch.arange(cs.numel())
+            if chunk_range is not None:
+                ids = ids[chunk_range[0]:chunk_range[1]]
+            sel = torch.zeros(base.numel(), dtype=torch.bool, device=base.device)
+            for c in ids.tolist():
+                sel[int(cs[c]):int(cs[c]) + int(cl[c])] = True
+        for o in list(outs_f32) + list(outs_bf16 or []):
             if o is not None:
-                o.copy_(tmp)
-        for o in outs_bf16 or []:
-            if o is not None:
-                o.copy_(tmp.to(o.dtype))
+                if sel is None:
+                    o.copy_(tmp.to(o.dtype))
+                else:
+                    o[sel] = tmp[sel].to(o.dtype)
         return outs_f32[0]
     cs, cl, ct = manifest.seg_table(base.device)
-    c0, c1 = chunk_range if chunk_range is not None else (0, cs.numel())
+    c0, c1 = chunk_range if chunk_range is not None else (0, cs.numel() if chunk_ids is None else chunk_ids.numel())
     if mode is None:
         d0 = deltas[0]
         mode = 2 if dscales is not None else DELTA_MODES[d0.dtype]
@@ -359,7 +382,8 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
         _ptr_array([_dp(d) for d in deltas]), _ptr_array([_dp(s) for s in dscales]) if dscales is not None else None,
         _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None, ctypes.c_uint32(wait_value),
         _lib.ptr(base), _lib.ptr(w), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(ct), c0, c1, _ptr_array(of), _ptr_array(ob),
-        n_out, _lib.ptr(nan_flags), _lib.ptr(error_flag), N, P, mode, grid or _lib.num_sms() * 8, _lib.stream_ptr())
+        n_out, _lib.ptr(nan_flags), _lib.ptr(error_flag), N, P, mode, grid or _lib.num_sms() * 8, _lib.stream_ptr(),
+        _lib.ptr(chunk_ids), int(unit_base))
     _c(rc, "gather_avg")
     _tick()
     return outs_f32[0]

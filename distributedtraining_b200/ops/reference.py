@@ -28,11 +28,14 @@ def dgelu_tanh(x: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=1):
+         splits=1, b2=None, b_persist=None):
     """out[M,N] = epi(alpha * A @ B^T).  ``a`` is stored [M,K] (K-major) or [K,M] (``a_mn``); ``b`` [N,K] or [K,N]."""
     A = a.t() if a_mn else a
-    Bt = b if b_mn else b.t()
-    acc = (A.float() @ Bt.float()) * alpha
+    if b_persist is not None:
+        b_persist.copy_(b)
+    bb = b.float() + b2.float() if b2 is not None else b.float()
+    Bt = bb if b_mn else bb.t()
+    acc = (A.float() @ Bt) * alpha
     if epi in ("bias", "bias_gelu", "bias_resid"):
         acc = acc + bias.float()
     if epi == "bias_gelu":

@@ -170,17 +170,49 @@ class ModelValidator:
 
 
 class DeltaValidator(ModelValidator):
-    """theta <- delta + theta (reference :251-259), fused: one kernel writes base+delta into master AND the bf16 copy."""
+    """theta <- delta + theta (reference :251-259).
+
+    Fused form (``fused_eval=True``, delta stored in the compute dtype -- bf16 windows on a B200): ``theta_base + delta_i``
+    is NEVER materialised for the weight matrices.  Every eval GEMM computes ``x (W + dW_i)^T`` as two accumulating
+    tcgen05 passes with ``dW_i`` read straight from miner i's peer window over NVLink (csrc/sm100_gemm.cu, dual-B), the
+    embedding adds the delta rows on the fly, and only the non-matrix tensors (< 1 % of the bytes) are updated by the
+    fused apply kernel restricted to their chunks.  Otherwise: one fused kernel writes base+delta into master AND the
+    bf16 copy (N = 1, w = 1)."""
+
+    def __init__(self, *a, fused_eval: bool = True, **kw):
+        self.fused_eval = fused_eval
+        self._fused_delta = None
+        super().__init__(*a, **kw)
+
+    def _ones(self):
+        m = self.model
+        return torch.ones(1, len(m.man), dtype=torch.float32, device=m.master.device)
 
     def update_model_weights(self, weight_deltas, alpha: float = 5e-4) -> None:
         m = self.model
         d = self._as_flat(weight_deltas)
-        if getattr(m, "is_cuda", False) and isinstance(d, torch.Tensor) and d.is_cuda:
-            w = torch.ones(1, len(m.man), dtype=torch.float32, device=m.master.device)
-            ops.weighted_avg(m.base, [d], w, m.man, [m.master], [m.p16])  # N = 1, w = 1: theta_base + delta
+        eng = getattr(m, "engine", None)
+        same_dev = isinstance(d, torch.Tensor) and d.device == m.master.device
+        if self.fused_eval and eng is not None and same_dev and d.dtype == m.p16.dtype:
+            ops.weighted_avg(m.base, [d], self._ones(), m.man, [m.master], [m.p16] if m.is_cuda else None,
+                             chunk_ids=eng.small_chunk_ids(), unit_base=True)
+            eng.set_delta(d)
+            self._fused_delta = d
+        elif getattr(m, "is_cuda", False) and same_dev:
+            ops.weighted_avg(m.base, [d], self._ones(), m.man, [m.master], [m.p16], unit_base=True)
         else:
             m.master.copy_(m.base + d.to(m.master.device, torch.float32))
             self._sync_compute_copy()
+
+    def restore_base(self) -> None:
+        m = self.model
+        if self._fused_delta is not None:
+            m.engine.set_delta(None)
+            ops.weighted_avg(m.base, [self._fused_delta], torch.zeros_like(self._ones()), m.man, [m.master],
+                             [m.p16] if m.is_cuda else None, chunk_ids=m.engine.small_chunk_ids(), unit_base=True)
+            self._fused_delta = None
+        else:
+            super().restore_base()
 
 
 class LocalValidator(ModelValidator):

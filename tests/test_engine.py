@@ -106,3 +106,42 @@ def test_trainer_graph_equals_eager_gpu():
     assert max(abs(a - b) for a, b in zip(out[0][0], out[1][0])) < 2e-3
     assert (out[0][1] - out[1][1]).abs().max().item() < 1e-3
     assert out[0][0][-1] < out[0][0][0] + 0.5
+
+
+@pytest.mark.parametrize("name", ["gpt2-tiny", "llama-tiny"])
+def test_fused_delta_and_peer_source_forward(name):
+    """dual-B (x (W+dW)^T without materialising W+dW) and persist-B (weights pulled from a source arena and persisted as
+    a side effect of the forward GEMMs) give the same loss as the materialised model.  CPU: reference ops."""
+    torch.manual_seed(0)
+    cfg, man, arena = new_model(name)
+    base = arena.flat.clone()
+    delta = torch.randn_like(base) * 0.01
+    B, T = 2, 16
+    ids = torch.randint(0, cfg.vocab_size, (B, T), dtype=torch.int32)
+    # oracle: materialised base + delta
+    eng = TransformerEngine(cfg, man, (base + delta).clone(), None, B, T, lm_chunk=32)
+    eng.set_batch(ids)
+    want = float(eng.forward_loss())
+    # fused delta: matrices stay at base, small tensors get base+delta through the chunk-restricted apply kernel
+    p = base.clone()
+    eng2 = TransformerEngine(cfg, man, p, None, B, T, lm_chunk=16)
+    ops.weighted_avg(base, [delta], torch.ones(1, len(man)), man, [p], chunk_ids=eng2.small_chunk_ids(), unit_base=True)
+    big = man[cfg.family == "gpt2" and "transformer.h.0.mlp.c_fc.weight" or "model.layers.0.mlp.down_proj.weight"]
+    assert torch.equal(p[big.offset:big.offset + big.numel], base[big.offset:big.offset + big.numel])
+    eng2.set_delta(delta)
+    eng2.set_batch(ids)
+    assert abs(float(eng2.forward_loss()) - want) < 1e-5
+    eng2.set_delta(None)
+    ops.weighted_avg(base, [delta], torch.zeros(1, len(man)), man, [p], chunk_ids=eng2.small_chunk_ids(), unit_base=True)
+    assert torch.allclose(p, base)
+    # peer source + persist
+    local = torch.zeros_like(base)
+    eng3 = TransformerEngine(cfg, man, local, None, B, T, lm_chunk=16)
+    eng3.set_source((base + delta).clone())
+    eng3.set_batch(ids)
+    assert abs(float(eng3.forward_loss()) - want) < 1e-5
+    eng3.persist_small_from_source()
+    eng3.set_source(None)
+    for sp in man:  # every tensor arrived as a side effect of the first forward (arena padding is not transported)
+        assert torch.allclose(man.view(local, sp.name), man.view(base + delta, sp.name)), sp.name
+    assert abs(float(eng3.forward_loss()) - want) < 1e-5

@@ -265,3 +265,22 @@ def test_weighted_avg_nan_screen():
     out = torch.empty(n, device=DEV)
     ops.weighted_avg(base, deltas, w, man, [out], nan_flags=nan)
     assert nan.tolist() == [0, 1, 0]
+
+
+def test_gemm_dual_b_and_persist():
+    """C = A (B + B2)^T in two accumulating passes; B tiles persisted to a local copy while being consumed."""
+    torch.manual_seed(11)
+    M, N, K = 640, 768, 320
+    A, B, B2 = _bf(M, K, scale=0.5), _bf(N, K, scale=0.5), _bf(N, K, scale=0.05)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, out, b2=B2)
+    _close(out, A.float() @ (B.float() + B2.float()).t(), rtol=1e-2)
+    dst = torch.zeros_like(B)
+    ops.gemm(A, B, out, b_persist=dst)
+    assert torch.equal(dst, B)
+    _close(out, A.float() @ B.float().t(), rtol=1e-2)
+    # MN-major B (dgrad form) with persist
+    Bt = B.t().contiguous()
+    dst2 = torch.zeros_like(Bt)
+    ops.gemm(A, Bt, out, b_mn=True, b_persist=dst2)
+    assert torch.equal(dst2, Bt)
