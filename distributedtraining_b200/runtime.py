@@ -66,6 +66,9 @@ def build_context(role: str, argv=None, config: Optional[Config] = None) -> Cont
     else:
         exchange = DiskExchange(cfg.storage.model_dir, rank, man, cfg.delta_dtype if cfg.delta_dtype != "fp8" else "bf16")
         scheme = "disk"
+    if cfg.inject:  # fault injection on the named ranks (utils/fault_injection.py)
+        from .utils.fault_injection import FaultyExchange, parse_inject
+        exchange = FaultyExchange(exchange, rank, parse_inject(cfg.inject))
     my_repo = cfg.storage.my_repo_id or f"{scheme}://{rank}"
     hf = HFManager(local_dir=cfg.storage.gradient_dir, my_repo_id=my_repo if role == "miner" else None,
                    averaged_model_repo_id=cfg.storage.averaged_model_repo_id, model_dir=cfg.storage.model_dir,
