@@ -216,23 +216,26 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
 
 // Fast path (d = VPL * 256): per-lane column partials for dw/db stay in REGISTERS across all rows of the warp and are
 // flushed once per warp (shared-memory atomics) and once per block (global atomics).
-template <bool RMS, int VPL>
+template <bool RMS, int VPL, bool COL>
 __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* __restrict__ dresid,
                                                             bf16* __restrict__ dx, float* __restrict__ dw,
-                                                            float* __restrict__ db, int M) {
+                                                            float* __restrict__ db, int M, float* __restrict__ dcol) {
   constexpr int d = VPL * 256;
-  extern __shared__ float sm[];  // [2][d]
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
+  extern __shared__ float sm[];  // [3][d]: dw | db | column sums of dresid (bias grad of the producing GEMM)
+  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  float ww[VPL][8], adw[VPL][8], adb[VPL][8];
+  float ww[VPL][8], adw[VPL][8], adb[VPL][8], adc[COL ? VPL : 1][8];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     unpack8(__ldg(reinterpret_cast<const uint4*>(w) + lane + 32 * j), ww[j]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) adw[j][k] = adb[j][k] = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      adw[j][k] = adb[j][k] = 0.f;
+      if (COL) adc[j][k] = 0.f;
+    }
   }
   for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
@@ -266,7 +269,10 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = (g[j][k] - s1 - xh[j][k] * s2) * rs;
-        if (rr) v += r[k];
+        if (rr) {
+          v += r[k];
+          if (COL) adc[j][k] += r[k];
+        }
         g[j][k] = v;
       }
       o[lane + 32 * j] = pack8(g[j]);
@@ -278,11 +284,13 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&sm[(lane + 32 * j) * 8 + k], adw[j][k]);
       if (!RMS) atomicAdd(&sm[d + (lane + 32 * j) * 8 + k], adb[j][k]);
+      if (COL) atomicAdd(&sm[2 * d + (lane + 32 * j) * 8 + k], adc[j][k]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     atomicAdd(&dw[i], sm[i]);
     if (!RMS && db) atomicAdd(&db[i], sm[d + i]);
+    if (COL && dcol) atomicAdd(&dcol[i], sm[2 * d + i]);
   }
 }
 
@@ -290,76 +298,91 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
 // fused cross-entropy: one CTA per row; the row is pulled into shared memory once (<= ~100 KB for V = 50k bf16),
 // loss = lse - logit[target]; logits are overwritten in place with (softmax - onehot) * scale.
 // ------------------------------------------------------------------------------------------------------------------
+// CACHE = true : the row is staged in shared memory while the online (max, sum-exp) pass runs -> 1 global read + 1 write.
+// CACHE = false: vocabularies whose row does not fit (Llama: 128 256 x bf16 = 250 KB) re-read the row from L2/HBM.
+template <bool CACHE>
 __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ targets,
                                                          float* __restrict__ losses, int V, int ldl, float grad_scale,
                                                          int write_grad) {
   extern __shared__ uint4 srow[];
-  __shared__ float red[32];
+  __shared__ float red_m[16], red_s[16];
   const int row = blockIdx.x;
   bf16* lr = logits + size_t(row) * ldl;
   const int tgt = targets[row];
   const int nvec = (V + 7) / 8;
   const uint4* src = reinterpret_cast<const uint4*>(lr);
-  float mx = -CUDART_INF_F;
+  // ---- pass 1: online softmax statistics (one exp per element + one rescale per 8) ----
+  float m = -CUDART_INF_F, ssum = 0.f;
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    uint4 q = src[i];
-    srow[i] = q;
+    const uint4 q = src[i];
+    if (CACHE) srow[i] = q;
     float a[8];
     unpack8(q, a);
+    float lm = -CUDART_INF_F;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (i * 8 + k < V) mx = fmaxf(mx, a[k]);
+    for (int k = 0; k < 8; ++k) {
+      if (i * 8 + k >= V) a[k] = -CUDART_INF_F;
+      lm = fmaxf(lm, a[k]);
+    }
+    const float mn = fmaxf(m, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += __expf(a[k] - mn);
+    ssum = ssum * __expf(m - mn) + acc;
+    m = mn;
   }
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  // combine (m, s) pairs: warp, then block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float mn = fmaxf(m, m2);
+    ssum = (mn == -CUDART_INF_F) ? 0.f : ssum * __expf(m - mn) + s2 * __expf(m2 - mn);
+    m = mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_m[threadIdx.x >> 5] = m;
+    red_s[threadIdx.x >> 5] = ssum;
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -CUDART_INF_F;
-    v = warp_max(v);
-    if (threadIdx.x == 0) red[0] = v;
-  }
-  __syncthreads();
-  mx = red[0];
-  __syncthreads();
-  float se = 0.f;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    float a[8];
-    unpack8(srow[i], a);
+    const int nw = blockDim.x >> 5;
+    m = threadIdx.x < nw ? red_m[threadIdx.x] : -CUDART_INF_F;
+    ssum = threadIdx.x < nw ? red_s[threadIdx.x] : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (i * 8 + k < V) se += __expf(a[k] - mx);
+    for (int o = 8; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+      const float mn = fmaxf(m, m2);
+      ssum = (mn == -CUDART_INF_F) ? 0.f : ssum * __expf(m - mn) + s2 * __expf(m2 - mn);
+      m = mn;
+    }
+    if (threadIdx.x == 0) {
+      red_m[0] = m;
+      red_s[0] = ssum;
+    }
   }
-  se = warp_sum(se);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) red[0] = v;
-  }
-  __syncthreads();
-  se = red[0];
+  const float mx = red_m[0], se = red_s[0];
   const float lse = mx + __logf(se);
   const bool valid = tgt >= 0;
   if (threadIdx.x == 0) {
-    float lt = valid ? __bfloat162float(reinterpret_cast<const bf16*>(srow)[tgt]) : 0.f;
+    const float lt = valid ? __bfloat162float(CACHE ? reinterpret_cast<const bf16*>(srow)[tgt] : lr[tgt]) : 0.f;
     losses[row] = valid ? (lse - lt) : 0.f;
   }
   if (!write_grad) return;
+  // ---- pass 2: dlogits = (softmax - onehot) * scale, in place ----
   const float sc = valid ? grad_scale : 0.f;
-  const float inv = 1.f / se;
   uint4* dst = reinterpret_cast<uint4*>(lr);
   const int nvec_pad = ldl / 8;
   for (int i = threadIdx.x; i < nvec_pad; i += blockDim.x) {
     float a[8];
     if (i < nvec) {
-      unpack8(srow[i], a);
+      unpack8(CACHE ? srow[i] : src[i], a);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = i * 8 + k;
-        float p = (c < V) ? __expf(a[k] - mx) * inv : 0.f;
-        if (c == tgt) p -= 1.f;
-        a[k] = p * sc;
+        float pr = (c < V) ? __expf(a[k] - lse) : 0.f;
+        if (c == tgt) pr -= 1.f;
+        a[k] = pr * sc;
       }
     } else {
 #pragma unroll
@@ -481,19 +504,27 @@ extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* o
 }
 template <bool RMS, int VPL>
 static void launch_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
-                                 const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s) {
-  const size_t smem = size_t(2) * VPL * 256 * sizeof(float);
-  norm_bwd_fast_kernel<RMS, VPL><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
-                                                         (const bf16*)dresid, (bf16*)dx, dw, db, M);
+                                 const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
+                                 float* dcol) {
+  const size_t smem = size_t(3) * VPL * 256 * sizeof(float);
+  if (dcol)
+    norm_bwd_fast_kernel<RMS, VPL, true><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
+                                                                 (const bf16*)dresid, (bf16*)dx, dw, db, M, dcol);
+  else
+    norm_bwd_fast_kernel<RMS, VPL, false><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
+                                                                  (const bf16*)dresid, (bf16*)dx, dw, db, M, nullptr);
 }
 extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                             const void* dresid, void* dx, float* dw, float* db, int M, int d, int rms, int num_sms,
-                            cudaStream_t s) {
+                            cudaStream_t s, float* dcol) {
+  // dcol (optional): += column sums of dresid, i.e. the bias gradient of the GEMM that produced the residual branch.
+  // Folded into this pass for d = 768 (register budget); otherwise the caller falls back to dtb_colsum.
+  if (dcol && !(d == 768 && dresid)) return 7;
   const int grid = min((M + 7) / 8, num_sms * 2);
 #define FAST(V)                                                                                             \
   if (d == V * 256 && (rms || V < 8)) {                                                                     \
-    if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s);            \
-    else launch_norm_bwd_fast<false, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s);               \
+    if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);      \
+    else launch_norm_bwd_fast<false, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);         \
     return KCHECK();                                                                                        \
   }
   FAST(3) FAST(4) FAST(8)
@@ -515,12 +546,16 @@ extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const 
 extern "C" int dtb_ce_fwd_bwd(void* logits, const int* targets, float* losses, int M, int V, int ldl, float grad_scale,
                               int write_grad, cudaStream_t s) {
   const size_t smem = size_t((V + 7) / 8) * 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(ce_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return 2;
-    configured = smem;
+  if (smem <= 110 * 1024) {  // two CTAs per SM keep the load/compute phases of different rows overlapped
+    static size_t configured = 0;
+    if (smem > configured) {
+      if (cudaFuncSetAttribute(ce_fwd_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return 2;
+      configured = smem;
+    }
+    ce_fwd_bwd_kernel<true><<<M, 512, smem, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
+  } else {
+    ce_fwd_bwd_kernel<false><<<M, 512, 0, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
   }
-  ce_fwd_bwd_kernel<<<M, 512, smem, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
   return KCHECK();
 }
 extern "C" int dtb_colsum(const void* x, float* out, int M, int N, int ldx, cudaStream_t s) {

@@ -12,6 +12,7 @@
 // Parity: reference hivetrain/training_manager.py:391,417-421 (AdamW, delta emit), hivetrain/averaging_logic.py:
 // 422-448 (weighted average), :513-528 (meta-gradient), :121-127 (NaN screen); SURVEY.md K10, K13, K19-K24.
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
@@ -176,18 +177,32 @@ struct AvgParams {
   int chunk_begin, chunk_end;          // shard of the chunk table (or of chunk_ids) processed by this launch
   const int32_t* chunk_ids;            // optional indirection: process chunk_ids[chunk_begin..chunk_end)
   int unit_base;                       // 1: theta = base + sum_i w_i delta_i (delta APPLY), 0: s_j = sum_i w_ij (averaging)
+  int ld_mode;                         // peer-load flavour, see ld_peer_v4
   uint32_t wait_value;
 };
 
+// Peer-load flavour (set once per process through DTB200_PEER_LD = sys | nc | weak; default sys):
+//   sys  : ld.relaxed.sys     -- coherent with data a peer published before its release flag (strictly correct)
+//   nc   : ld.global.nc       -- non-coherent streaming path (L1 no-allocate); valid because a window buffer is never
+//                                 rewritten while a kernel that reads it is in flight (round-parity double buffering)
+//   weak : plain ld.global
+__device__ int g_peer_ld_mode = 0;
+DTB_DEVICE uint4 ld_peer_v4(const void* ptr, int mode) {
+  if (mode == 1) return ld_nc_v4(ptr);
+  if (mode == 2) return *reinterpret_cast<const uint4*>(ptr);
+  return ld_relaxed_sys_v4(ptr);
+}
+
 template <int MODE>
 __device__ __forceinline__ void load_delta8(const AvgParams& p, int i, size_t e, float* d) {
+  const int lm = p.ld_mode;
   if (MODE == 0) {
-    const uint4 q0 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e);
-    const uint4 q1 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e + 4);
+    const uint4 q0 = ld_peer_v4(reinterpret_cast<const float*>(p.delta[i]) + e, lm);
+    const uint4 q1 = ld_peer_v4(reinterpret_cast<const float*>(p.delta[i]) + e + 4, lm);
     d[0] = __uint_as_float(q0.x); d[1] = __uint_as_float(q0.y); d[2] = __uint_as_float(q0.z); d[3] = __uint_as_float(q0.w);
     d[4] = __uint_as_float(q1.x); d[5] = __uint_as_float(q1.y); d[6] = __uint_as_float(q1.z); d[7] = __uint_as_float(q1.w);
   } else if (MODE == 1) {
-    const uint4 q = ld_relaxed_sys_v4(reinterpret_cast<const bf16*>(p.delta[i]) + e);
+    const uint4 q = ld_peer_v4(reinterpret_cast<const bf16*>(p.delta[i]) + e, lm);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -501,6 +516,14 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
   p.nan_flags = nan_flags; p.error_flag = error_flag; p.N = N; p.P = P; p.n_out = n_out; p.mode = mode;
   p.chunk_begin = chunk_begin; p.chunk_end = chunk_end; p.wait_value = wait_flags ? wait_value : 0;
   p.chunk_ids = chunk_ids; p.unit_base = unit_base;
+  {
+    static int mode = -1;
+    if (mode < 0) {
+      const char* e = getenv("DTB200_PEER_LD");
+      mode = (e && e[0] == 'n') ? 1 : ((e && e[0] == 'w') ? 2 : 0);
+    }
+    p.ld_mode = mode;
+  }
   if (grid > chunk_end - chunk_begin) grid = chunk_end - chunk_begin;
   if (grid < 1) return 0;
   if (mode == 0) gather_avg_kernel<0><<<grid, 256, 0, s>>>(p);

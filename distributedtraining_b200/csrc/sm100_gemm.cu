@@ -14,6 +14,7 @@
 // (reference hivetrain/training_manager.py:380-386).
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -85,7 +86,10 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+// CL = thread-block-cluster size along M (1 or 2).  With CL = 2 the two CTAs work on vertically adjacent output tiles that
+// share the B tile: each CTA TMA-loads half of it and MULTICASTS it into both CTAs' shared memory, cutting L2->SM traffic
+// per tile pair from 96 KB to 64 KB per k-block (the measured ceiling of the 1-CTA kernel).
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmap_aux);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.persist_b ? 2 : 1);
+      mbar_init(&empty_bar[i], CL > 1 ? CL : (p.persist_b ? 2 : 1));
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -124,19 +128,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers must not multicast into / arrive on uninitialised barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const int tiles_mg = (p.tiles_m + CL - 1) / CL;  // M-tile groups; CTA r of a cluster owns m_t = mg * CL + r
+  const int total_work = tiles_mg * p.tiles_n * p.splits;
+  constexpr uint16_t kMcMask = uint16_t((1u << CL) - 1);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int n_t = w % p.tiles_n;
-        const int m_t = (w / p.tiles_n) % p.tiles_m;
-        const int sp = w / (p.tiles_n * p.tiles_m);
+        const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
+        const int sp = w / (p.tiles_n * tiles_mg);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
@@ -155,7 +164,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             } else {
               tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
             }
-            if constexpr (B_MN) {
+            if constexpr (CL > 1) {  // my share of the B tile, multicast to every CTA of the cluster
+              if constexpr (B_MN) {
+                constexpr int kPer = (BLOCK_N / 64) / CL;
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                  const int a = cta_rank * kPer + i;
+                  tma_load_2d_mc(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0, kMcMask);
+                }
+              } else {
+                constexpr int kRows = BLOCK_N / CL;
+                tma_load_2d_mc(sb + cta_rank * (kRows * 128), bmap, &full_bar[stage], k0, n0 + cta_rank * kRows, kMcMask);
+              }
+            } else if constexpr (B_MN) {
 #pragma unroll
               for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0);
             } else {
@@ -175,8 +196,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     constexpr uint32_t a_kadv = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;  // descriptor start-address units (16 B)
     constexpr uint32_t b_kadv = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int sp = w / (p.tiles_n * p.tiles_m);
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      const int sp = w / (p.tiles_n * tiles_mg);
       const int kb0 = sp * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -195,7 +216,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], kMcMask);  // the stage is free once EVERY CTA consumed it
+          else umma_commit(&empty_bar[stage]);
           if (ki == nk - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
@@ -209,10 +231,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     // to the local weight copy while the MMA consumes it: the broadcast rides on the first forward GEMM.
     if (p.persist_b && lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int n_t = w % p.tiles_n;
-        const int m_t = (w / p.tiles_n) % p.tiles_m;
-        const int sp = w / (p.tiles_n * p.tiles_m);
+        const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
+        const int sp = w / (p.tiles_n * tiles_mg);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int n0 = n_t * BLOCK_N;
@@ -256,9 +278,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
     const bool has_aux = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
     const bool dual = (p.epi == EPI_BIAS_GELU);
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
       const int n_t = w % p.tiles_n;
-      const int m_t = (w / p.tiles_n) % p.tiles_m;
+      const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
       const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
       if (has_bias) {
         named_bar_sync(3, kEpiThreads);  // previous tile's readers of smem_bias are done
@@ -397,6 +419,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into its shared memory
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -437,17 +460,42 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inn
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL>
 static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32>;
+  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int CL>
+static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn, bool out_f32, cudaStream_t stream) {
+  if (out_f32) {
+    if (a_mn && b_mn) return launch<true, true, true, CL>(p, grid, stream);
+    if (!a_mn && b_mn) return launch<false, true, true, CL>(p, grid, stream);
+    if (!a_mn && !b_mn) return launch<false, false, true, CL>(p, grid, stream);
+    return launch<true, false, true, CL>(p, grid, stream);
+  }
+  if (a_mn && b_mn) return launch<true, true, false, CL>(p, grid, stream);
+  if (!a_mn && b_mn) return launch<false, true, false, CL>(p, grid, stream);
+  if (!a_mn && !b_mn) return launch<false, false, false, CL>(p, grid, stream);
+  return launch<true, false, false, CL>(p, grid, stream);
 }
 
 }  // namespace dtb
@@ -461,10 +509,14 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   using namespace dtb;
   GemmParams p;
   int rc = 0;
+  const int tiles_m_ = (M + BLOCK_M - 1) / BLOCK_M, tiles_n_ = (N + BLOCK_N - 1) / BLOCK_N;
+  static const int force_cl = getenv("DTB200_GEMM_CLUSTER") ? atoi(getenv("DTB200_GEMM_CLUSTER")) : 0;
+  int CL = (!b2 && !b_persist && tiles_m_ >= 2 && tiles_m_ * tiles_n_ >= 32) ? 2 : 1;
+  if (force_cl == 1 || b2 || b_persist) CL = 1;
   if (a_mn) rc |= make_tmap_2d(&p.tmap_a, a, 2, M, K, lda, 64, BLOCK_K);
   else      rc |= make_tmap_2d(&p.tmap_a, a, 2, K, M, lda, BLOCK_K, BLOCK_M);
   if (b_mn) rc |= make_tmap_2d(&p.tmap_b, b, 2, N, K, ldb, 64, BLOCK_K);
-  else      rc |= make_tmap_2d(&p.tmap_b, b, 2, K, N, ldb, BLOCK_K, BLOCK_N);
+  else      rc |= make_tmap_2d(&p.tmap_b, b, 2, K, N, ldb, BLOCK_K, BLOCK_N / CL);
   if (out_f32) rc |= make_tmap_2d(&p.tmap_c, c, 4, N, M, ldc, 32, BLOCK_M);
   else         rc |= make_tmap_2d(&p.tmap_c, c, 2, N, M, ldc, 64, BLOCK_M);
   if (c2) rc |= make_tmap_2d(&p.tmap_c2, c2, 2, N, M, ldc2, 64, BLOCK_M);
@@ -499,20 +551,12 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.ldaux = ldaux;
   p.alpha = alpha;
-  int total = p.tiles_m * p.tiles_n * p.splits;
-  int grid = total < num_sms ? total : num_sms;
-  if (grid < 1) return 0;
-  cudaError_t e;
-  if (out_f32) {
-    if (a_mn && b_mn) e = launch<true, true, true>(p, grid, stream);
-    else if (!a_mn && b_mn) e = launch<false, true, true>(p, grid, stream);
-    else if (!a_mn && !b_mn) e = launch<false, false, true>(p, grid, stream);
-    else e = launch<true, false, true>(p, grid, stream);
-  } else {
-    if (a_mn && b_mn) e = launch<true, true, false>(p, grid, stream);
-    else if (!a_mn && b_mn) e = launch<false, true, false>(p, grid, stream);
-    else if (!a_mn && !b_mn) e = launch<false, false, false>(p, grid, stream);
-    else e = launch<true, false, false>(p, grid, stream);
-  }
+  const int tiles_mg = (p.tiles_m + CL - 1) / CL;
+  int total = tiles_mg * p.tiles_n * p.splits;   // work items per cluster
+  int max_clusters = num_sms / CL;
+  int nclusters = total < max_clusters ? total : max_clusters;
+  if (nclusters < 1) return 0;
+  int grid = nclusters * CL;
+  cudaError_t e = CL == 2 ? dispatch<2>(p, grid, a_mn, b_mn, out_f32, stream) : dispatch<1>(p, grid, a_mn, b_mn, out_f32, stream);
   return e == cudaSuccess ? 0 : int(e);
 }

@@ -306,9 +306,9 @@ class TransformerEngine:
         else:
             ops.rmsnorm_fwd(x, w, self.cfg.eps, out, rstd)
 
-    def _norm_bwd(self, dy, x, w, mean, rstd, dx_out, dw, db, dresid):
+    def _norm_bwd(self, dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol=None):
         if self.cfg.family == "gpt2":
-            ops.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
+            ops.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol)
         else:
             ops.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
 
@@ -447,19 +447,17 @@ class TransformerEngine:
                 ops.gemm(dx, Lp.proj_w, self.dact, b_mn=True)
                 ops.swiglu_bwd(self.dact, self.u[l], self.du)
             ops.gemm(dx, self.act[l], Lg.proj_w, a_mn=True, b_mn=True, accumulate=True)
-            if Lg.proj_b is not None:
-                ops.colsum(dx, Lg.proj_b)
             ops.gemm(self.du, Lp.fc_w, self.dh, b_mn=True)
             ops.gemm(self.du, self.h2[l], Lg.fc_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.fc_b is not None:
                 ops.colsum(self.du, Lg.fc_b)
-            self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx)
+            # d(proj bias) = colsum(dx) rides on this pass (dx is its residual input)
+            self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx,
+                           Lg.proj_b)
             dx, dx2 = dx2, dx
             # ---- attention block ----
             ops.gemm(dx, Lp.o_w, self.datt, b_mn=True)
             ops.gemm(dx, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
-            if Lg.o_b is not None:
-                ops.colsum(dx, Lg.o_b)
             ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv)
             if cfg.family == "llama":
                 ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
@@ -467,7 +465,7 @@ class TransformerEngine:
             ops.gemm(self.dqkv, self.h1[l], Lg.qkv_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.qkv_b is not None:
                 ops.colsum(self.dqkv, Lg.qkv_b)
-            self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx)
+            self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx, Lg.o_b)
             dx, dx2 = dx2, dx
         ops.embed_bwd(dx, self.ids, G.wte, G.wpe)
         return self.loss

@@ -126,13 +126,20 @@ def layernorm_fwd(x, w, b, eps, out, mean, rstd):
     return out
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None):
+def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None, dcol=None):
+    """``dcol`` (fp32 [d], optional): += column sums of ``dresid`` -- the bias gradient of the GEMM that fed the residual
+    branch, folded into this pass instead of a separate colsum launch."""
     if not use_kernels(dx_out):
+        if dcol is not None:
+            ref.colsum(dresid, dcol)
         return ref.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
     M, d = x.shape
+    fold = dcol is not None and d == 768 and dresid is not None
+    if dcol is not None and not fold:
+        colsum(dresid, dcol)
     _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dresid),
-                               _lib.ptr(dx_out), _lib.ptr(dw), _lib.ptr(db), M, d, 0, _lib.num_sms(), _lib.stream_ptr()),
-       "layernorm_bwd")
+                               _lib.ptr(dx_out), _lib.ptr(dw), _lib.ptr(db), M, d, 0, _lib.num_sms(), _lib.stream_ptr(),
+                               _lib.ptr(dcol) if fold else None), "layernorm_bwd")
     _tick()
     return dx_out
 
@@ -152,7 +159,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid=None):
         return ref.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
     M, d = x.shape
     _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), None, _lib.ptr(rstd), _lib.ptr(dresid),
-                               _lib.ptr(dx_out), _lib.ptr(dw), None, M, d, 1, _lib.num_sms(), _lib.stream_ptr()),
+                               _lib.ptr(dx_out), _lib.ptr(dw), None, M, d, 1, _lib.num_sms(), _lib.stream_ptr(), None),
        "rmsnorm_bwd")
     _tick()
     return dx_out

@@ -235,9 +235,11 @@ class PeerExchange(Exchange):
         return int(self.win.flags()[self.F_DELTA + src].item())
 
     def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
-        flags = self.win.flags()
-        if int(flags[self.F_DELTA + src].item()) < round:
-            return None  # stale flag == failed download in the reference
+        latest = int(self.win.flags()[self.F_DELTA + src].item())
+        if latest < max(round, 1):
+            return None  # stale flag / never published == failed download in the reference
+        if round <= 0:
+            round = latest  # "whatever the miner published last" (the reference downloads the repo head)
         d = self.delta_buf(round, src)[:self.man.total]
         if self.delta_dtype_name == "fp8":
             return ops.dequant_fp8(d, self.scale_buf(round, src))

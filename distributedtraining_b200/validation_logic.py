@@ -179,9 +179,14 @@ class DeltaValidator(ModelValidator):
     fused apply kernel restricted to their chunks.  Otherwise: one fused kernel writes base+delta into master AND the
     bf16 copy (N = 1, w = 1)."""
 
-    def __init__(self, *a, fused_eval: bool = True, **kw):
+    def __init__(self, *a, fused_eval: bool = False, **kw):
+        # fused_eval=False (default): ONE fused apply kernel (peer read) materialises base+delta_i, then plain eval GEMMs --
+        #   the faster choice when a miner is scored on many tokens (the reference evaluates 51 200 tokens per miner):
+        #   the dual-B form spends two tensor-core passes per GEMM and is only ahead when the eval is weight-bandwidth
+        #   bound (few tokens per miner).  Measured: profiles/validator_bench_*.json.
         self.fused_eval = fused_eval
         self._fused_delta = None
+        self._dcache = None
         super().__init__(*a, **kw)
 
     def _ones(self):
@@ -194,6 +199,11 @@ class DeltaValidator(ModelValidator):
         eng = getattr(m, "engine", None)
         same_dev = isinstance(d, torch.Tensor) and d.device == m.master.device
         if self.fused_eval and eng is not None and same_dev and d.dtype == m.p16.dtype:
+            if m.is_cuda:  # one NVLink read: cache the peer delta locally, later batches hit HBM/L2 instead of the link
+                if self._dcache is None:
+                    self._dcache = torch.empty_like(m.p16)
+                self._dcache.copy_(d, non_blocking=True)
+                d = self._dcache
             ops.weighted_avg(m.base, [d], self._ones(), m.man, [m.master], [m.p16] if m.is_cuda else None,
                              chunk_ids=eng.small_chunk_ids(), unit_base=True)
             eng.set_delta(d)

@@ -66,7 +66,7 @@ def main():
         hf = HFManager(local_dir="/tmp/dtb_val", averaged_model_repo_id="avg", exchange=ex, manifest=tr.man)
         loader = list(SyntheticTokens(B, T, V, seed=4242, device=str(dev), pool=a.eval_batches, steps=a.eval_batches))
         res = {}
-        for mode in ("fused", "applied"):
+        for mode in ("applied", "fused"):
             val = DeltaValidator(dev, tr, None, loader, BittensorNetwork, hf, chain_manager=chain, fused_eval=(mode == "fused"))
             val.validate_and_score()  # warm-up
             torch.cuda.synchronize()
