@@ -244,10 +244,18 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
     const float rs = rstd[row];
     float g[VPL][8], xh[VPL][8];
     float s1 = 0.f, s2 = 0.f;
+    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
+    uint4 rq[VPL], gq[VPL], xq[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {  // all loads of the row are issued before any use
+      gq[j] = __ldg(dyr + lane + 32 * j);
+      xq[j] = __ldg(xr + lane + 32 * j);
+      if (rr) rq[j] = __ldg(rr + lane + 32 * j);
+    }
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      unpack8(__ldg(dyr + lane + 32 * j), g[j]);
-      unpack8(__ldg(xr + lane + 32 * j), xh[j]);
+      unpack8(gq[j], g[j]);
+      unpack8(xq[j], xh[j]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         xh[j][k] = (xh[j][k] - mu) * rs;
@@ -261,11 +269,10 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
     s1 = RMS ? 0.f : warp_sum(s1) * (1.f / d);
     s2 = warp_sum(s2) * (1.f / d);
     uint4* o = reinterpret_cast<uint4*>(dx + size_t(row) * d);
-    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       float r[8];
-      if (rr) unpack8(__ldg(rr + lane + 32 * j), r);
+      if (rr) unpack8(rq[j], r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = (g[j][k] - s1 - xh[j][k] * s2) * rs;
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
 // CACHE = true : the row is staged in shared memory while the online (max, sum-exp) pass runs -> 1 global read + 1 write.
 // CACHE = false: vocabularies whose row does not fit (Llama: 128 256 x bf16 = 250 KB) re-read the row from L2/HBM.
 template <bool CACHE>
-__global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ targets,
+__global__ void __launch_bounds__(512, 2) ce_fwd_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ targets,
                                                          float* __restrict__ losses, int V, int ldl, float grad_scale,
                                                          int write_grad) {
   extern __shared__ uint4 srow[];
@@ -313,23 +320,34 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(bf16* __restrict__ logi
   const uint4* src = reinterpret_cast<const uint4*>(lr);
   // ---- pass 1: online softmax statistics (one exp per element + one rescale per 8) ----
   float m = -CUDART_INF_F, ssum = 0.f;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const uint4 q = src[i];
-    if (CACHE) srow[i] = q;
-    float a[8];
-    unpack8(q, a);
-    float lm = -CUDART_INF_F;
+  constexpr int kBatch = 4;  // independent 16 B loads in flight per thread (the row is latency-, not bandwidth-bound)
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += blockDim.x * kBatch) {
+    uint4 q[kBatch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (i * 8 + k >= V) a[k] = -CUDART_INF_F;
-      lm = fmaxf(lm, a[k]);
+    for (int b = 0; b < kBatch; ++b) {
+      const int i = i0 + b * blockDim.x;
+      if (i < nvec) q[b] = src[i];
     }
-    const float mn = fmaxf(m, lm);
-    float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += __expf(a[k] - mn);
-    ssum = ssum * __expf(m - mn) + acc;
-    m = mn;
+    for (int b = 0; b < kBatch; ++b) {
+      const int i = i0 + b * blockDim.x;
+      if (i >= nvec) break;
+      if (CACHE) srow[i] = q[b];
+      float a[8];
+      unpack8(q[b], a);
+      float lm = -CUDART_INF_F;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (i * 8 + k >= V) a[k] = -CUDART_INF_F;
+        lm = fmaxf(lm, a[k]);
+      }
+      const float mn = fmaxf(m, lm);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += __expf(a[k] - mn);
+      ssum = ssum * __expf(m - mn) + acc;
+      m = mn;
+    }
   }
   // combine (m, s) pairs: warp, then block
 #pragma unroll

@@ -520,7 +520,7 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
     static int mode = -1;
     if (mode < 0) {
       const char* e = getenv("DTB200_PEER_LD");
-      mode = (e && e[0] == 'n') ? 1 : ((e && e[0] == 'w') ? 2 : 0);
+      mode = (e && e[0] == 'n') ? 1 : ((e && e[0] == 's') ? 0 : 2);  // default: weak (2x the link throughput of sys-scope loads, measured)
     }
     p.ld_mode = mode;
   }

@@ -15,6 +15,7 @@
 // Parity: replaces HF GPT-2's eager/SDPA attention inside the reference's model(...) / loss.backward()
 // (reference hivetrain/training_manager.py:380-386).
 #include <cstdint>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -577,6 +578,254 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// single-block fast paths: every 128-token block is self-contained (128 % T == 0 or T == 128: the reference miner's T = 64)
+// ------------------------------------------------------------------------------------------------------------------
+// forward: Q K V | P aliases Q+K (dead once S is computed);  TMEM: S[128], O reuses S[0:64]  -> 48 KB + 128 columns,
+// four CTAs per SM overlap each other's TMA / MMA / softmax phases.
+constexpr int kFwdSmallSmem = 1024 + kTile * 3 + 64;
+
+__global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTile;
+  uint8_t* sV = smem + 2 * kTile;
+  uint8_t* sP = smem;  // 2 atoms over Q|K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTile * 3);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qb = blockIdx.x, h = blockIdx.y;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qb * kBlk;
+  const int row_tok = q0 + tid;
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tmap_qkv);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_off = (uint32_t(warp) * 32u) << 16;
+  constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
+  constexpr uint32_t idesc_o = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 3 * kTile);
+    tma_load_2d(sQ, &p.tmap_qkv, &bars[0], h * kHd, q0);
+    tma_load_2d(sK, &p.tmap_qkv, &bars[0], (p.H + hk) * kHd, q0);
+    tma_load_2d(sV, &p.tmap_qkv, &bars[0], (p.H + p.Hkv + hk) * kHd, q0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024), dk = make_smem_desc(smem_u32(sK), 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(tmem, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
+    umma_commit(&bars[1]);
+  }
+  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_tok - q0;
+  const float sl2 = p.scale * kLog2e;
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  float mx = -CUDART_INF_F;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    // chunk-level mask test is warp-uniform only when T % 32 == 0; the load is collective, so always load
+    float sv[32];
+    tmem_ld32(tmem + lane_off + ch * 32, sv);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = ch * 32 + i;
+      if (c >= c_lo && c <= c_hi) mx = fmaxf(mx, sv[i]);
+    }
+  }
+  const float m_ref = mx * sl2;
+  float lsum = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float sv[32];
+    tmem_ld32(tmem + lane_off + ch * 32, sv);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = ch * 32 + i;
+      const float e = (c >= c_lo && c <= c_hi) ? exp2f(sv[i] * sl2 - m_ref) : 0.f;
+      sv[i] = e;
+      lsum += e;
+    }
+    // all 128 threads finished READING Q/K? they are only read by the tensor core, which completed (bars[1]) -> safe
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint4 q;
+      q.x = pack2(sv[v * 8 + 0], sv[v * 8 + 1]); q.y = pack2(sv[v * 8 + 2], sv[v * 8 + 3]);
+      q.z = pack2(sv[v * 8 + 4], sv[v * 8 + 5]); q.w = pack2(sv[v * 8 + 6], sv[v * 8 + 7]);
+      st_swz(sP + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, q);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < kBlk / 16; ++k) {
+      const uint64_t dp = make_smem_desc(smem_u32(sP) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+      const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 2048, kTile, 1024);
+      umma_f16(tmem, dp, dv, idesc_o, k > 0);  // O overwrites S[0:64] (every thread has consumed S)
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+  __nv_bfloat16* dst = p.out + size_t(row_tok) * p.ld_out + h * kHd;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    float o[32];
+    tmem_ld32(tmem + lane_off + ch * 32, o);
+    if (row_tok < p.M) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 q;
+        q.x = pack2(o[v * 8 + 0] * inv, o[v * 8 + 1] * inv); q.y = pack2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv);
+        q.z = pack2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv); q.w = pack2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[ch * 4 + v] = q;
+      }
+    }
+  }
+  if (row_tok < p.M && p.lse) {
+    const int b = row_tok / p.T, t = row_tok % p.T;
+    p.lse[(size_t(b) * p.H + h) * p.T + t] = (m_ref + log2f(lsum)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// backward, all five products in ONE CTA (no recomputation across kernels):
+//   S = Q K^T, dP = dO V^T  ->  P, dS  ->  dV = P^T dO, dK = dS^T Q, dQ = dS K.     (MHA only: H == Hkv)
+// smem: Q K V dO | P(2) | dS(2) = 128 KB; TMEM: S[128] dP[128] dV[64] dK[64] dQ[64] = 448 columns.
+constexpr int kBwdSmallSmem = 1024 + kTile * 8 + 64;
+
+__global__ void __launch_bounds__(128, 1) attn_bwd_small_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTile;
+  uint8_t* sV = smem + 2 * kTile;
+  uint8_t* sDO = smem + 3 * kTile;
+  uint8_t* sP = smem + 4 * kTile;
+  uint8_t* sDS = smem + 6 * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * kTile);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qb = blockIdx.x, h = blockIdx.y;
+  const int q0 = qb * kBlk;
+  const int row_tok = q0 + tid;
+  const int colQ = h * kHd, colK = (p.H + h) * kHd, colV = (2 * p.H + h) * kHd;
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tmap_qkv);
+    tma_prefetch_desc(&p.tmap_do);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const uint32_t lane_off = (uint32_t(warp) * 32u) << 16;
+  constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
+  constexpr uint32_t idesc_g = make_idesc(kFmtBF16, kFmtBF16, true, true, 128, 64);
+  constexpr uint32_t idesc_q = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 4 * kTile);
+    tma_load_2d(sQ, &p.tmap_qkv, &bars[0], colQ, q0);
+    tma_load_2d(sK, &p.tmap_qkv, &bars[0], colK, q0);
+    tma_load_2d(sV, &p.tmap_qkv, &bars[0], colV, q0);
+    tma_load_2d(sDO, &p.tmap_do, &bars[0], colQ, q0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024), dk = make_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t ddo = make_smem_desc(smem_u32(sDO), 16, 1024), dv = make_smem_desc(smem_u32(sV), 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(tS, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(tDP, ddo + uint64_t(k * 2), dv + uint64_t(k * 2), idesc_s, k > 0);
+    umma_commit(&bars[1]);
+  }
+  float Drow, lse_l2;
+  load_row_stats(p, row_tok, h, Drow, lse_l2);
+  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = (row_tok < p.M) ? row_tok - q0 : -1;
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, p.scale * kLog2e, lse_l2, Drow, p.scale, sP, sDS);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < kBlk / 16; ++k) {
+      umma_f16(tDV, make_smem_desc(smem_u32(sP) + k * 2048, kTile, 1024), make_smem_desc(smem_u32(sDO) + k * 2048, kTile, 1024),
+               idesc_g, k > 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kBlk / 16; ++k) {
+      umma_f16(tDK, make_smem_desc(smem_u32(sDS) + k * 2048, kTile, 1024), make_smem_desc(smem_u32(sQ) + k * 2048, kTile, 1024),
+               idesc_g, k > 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kBlk / 16; ++k) {
+      umma_f16(tDQ, make_smem_desc(smem_u32(sDS) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+               make_smem_desc(smem_u32(sK) + k * 2048, kTile, 1024), idesc_q, k > 0);
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  // thread = token row for all three outputs (q row for dQ, key row for dK/dV)
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    const uint32_t t = which == 0 ? tDQ : (which == 1 ? tDK : tDV);
+    __nv_bfloat16* dst = p.out + size_t(row_tok) * p.ld_out + (which == 0 ? colQ : (which == 1 ? colK : colV));
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      float o[32];
+      tmem_ld32(t + lane_off + ch * 32, o);
+      if (row_tok < p.M) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 q;
+          q.x = pack2(o[v * 8 + 0], o[v * 8 + 1]); q.y = pack2(o[v * 8 + 2], o[v * 8 + 3]);
+          q.z = pack2(o[v * 8 + 4], o[v * 8 + 5]); q.w = pack2(o[v * 8 + 6], o[v * 8 + 7]);
+          reinterpret_cast<uint4*>(dst)[ch * 4 + v] = q;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -593,10 +842,13 @@ extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   static bool cfg = false;
   if (!cfg) {
     if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess) return 12;
+    if (cudaFuncSetAttribute(attn_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmallSmem) != cudaSuccess) return 12;
     cfg = true;
   }
   dim3 grid((M + kBlk - 1) / kBlk, H);
-  attn_fwd_kernel<<<grid, 128, kFwdSmem, s>>>(p);
+  static const bool no_small = getenv("DTB200_ATTN_NO_SMALL") != nullptr;
+  if (kBlk % T == 0 && !no_small) attn_fwd_small_kernel<<<grid, 128, kFwdSmallSmem, s>>>(p);  // self-contained blocks
+  else attn_fwd_kernel<<<grid, 128, kFwdSmem, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -613,9 +865,15 @@ extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* 
   if (!cfg) {
     if (cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdKvSmem) != cudaSuccess) return 12;
     if (cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdQSmem) != cudaSuccess) return 12;
+    if (cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmallSmem) != cudaSuccess) return 12;
     cfg = true;
   }
   const int nblk = (M + kBlk - 1) / kBlk;
+  static const bool no_small = getenv("DTB200_ATTN_NO_SMALL") != nullptr;
+  if (kBlk % T == 0 && H == Hkv && !no_small) {
+    attn_bwd_small_kernel<<<dim3(nblk, H), 128, kBwdSmallSmem, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
   attn_bwd_kv_kernel<<<dim3(nblk, Hkv), 128, kBwdKvSmem, s>>>(p);
   if (cudaGetLastError() != cudaSuccess) return 1;
   attn_bwd_q_kernel<<<dim3(nblk, H), 128, kBwdQSmem, s>>>(p);

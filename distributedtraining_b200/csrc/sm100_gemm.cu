@@ -33,7 +33,9 @@ constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStageBytes = kABytes + kBBytes;       // 1-SM: 48 KB x 4 stages
+constexpr int kStages2 = 6;                          // 2-SM: (16 KB A + 16 KB half-B) x 6 stages
+constexpr int kStageBytes2 = kABytes + kBBytes / 2;
 constexpr int kSlabBytes = BLOCK_M * 128;       // 16 KB: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 constexpr int kNumSlabBufs = 2;
 constexpr int kTmemCols = 512;
@@ -86,19 +88,26 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// CL = thread-block-cluster size along M (1 or 2).  With CL = 2 the two CTAs work on vertically adjacent output tiles that
-// share the B tile: each CTA TMA-loads half of it and MULTICASTS it into both CTAs' shared memory, cutting L2->SM traffic
-// per tile pair from 96 KB to 64 KB per k-block (the measured ceiling of the 1-CTA kernel).
+// CL = 1: one CTA per 128x256 tile (cta_group::1).  Measured ceiling ~1.3 PF: TMA fills (96 B/clk) + tensor-core operand
+//         reads (96 B/clk) exceed the 128 B/clk shared-memory bandwidth of one SM.
+// CL = 2: 2-SM UMMA (cta_group::2): a CTA pair owns a 256x256 tile; each CTA stages its 128 A rows and HALF of the B tile
+//         (the tensor cores of the pair share operands), so per-SM shared-memory traffic drops to 64 + 64 B/clk and the
+//         ring deepens to 6 stages.  Only the pair's leader issues MMAs; TMA bytes of both CTAs are credited to the
+//         leader's full barrier; stage release / accumulator-ready are multicast commits; the non-leader's epilogue
+//         arrives remotely on the leader's TMEM-empty barrier.
 template <bool A_MN, bool B_MN, bool OUT_F32, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kNStages = CL == 2 ? kStages2 : kStages;
+  constexpr int kStgBytes = CL == 2 ? kStageBytes2 : kStageBytes;
+  static_assert(kStages2 * kStageBytes2 == kStages * kStageBytes, "same ring footprint");
   uint8_t* smem_ab = smem;
-  uint8_t* smem_slab = smem + kStages * kStageBytes;
+  uint8_t* smem_slab = smem + kNStages * kStgBytes;
   float* smem_bias = reinterpret_cast<float*>(smem_slab + kNumSlabBufs * kSlabBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BLOCK_N);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + kNStages;
+  uint64_t* tmem_full_bar = empty_bar + kNStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* aux_bars = tmem_empty_bar + 2;  // [2] one per epilogue group
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bars + 2);
@@ -111,20 +120,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmap_b);
     tma_prefetch_desc(&p.tmap_c);
     tma_prefetch_desc(&p.tmap_aux);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kNStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL > 1 ? CL : (p.persist_b ? 2 : 1));
+      mbar_init(&empty_bar[i], (CL == 1 && p.persist_b) ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiThreads / 32);
+      mbar_init(&tmem_empty_bar[i], CL * (kEpiThreads / 32));  // 2-SM: the epilogue warps of BOTH CTAs arrive on the leader
       mbar_init(&aux_bars[i], 1);
     }
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc(tmem_ptr_smem, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CL == 2) {
+      tmem_alloc_2sm(tmem_ptr_smem, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -137,6 +151,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   const int tiles_mg = (p.tiles_m + CL - 1) / CL;  // M-tile groups; CTA r of a cluster owns m_t = mg * CL + r
   const int total_work = tiles_mg * p.tiles_n * p.splits;
   constexpr uint16_t kMcMask = uint16_t((1u << CL) - 1);
+  const bool is_leader = cta_rank == 0;
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -154,49 +169,55 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           const CUtensorMap* bmap = rep == 0 ? &p.tmap_b : &p.tmap_b2;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem_ab + stage * kStageBytes;
+            uint8_t* sa = smem_ab + stage * kStgBytes;
             uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
             const int k0 = kb * BLOCK_K;
-            if constexpr (A_MN) {
+            if constexpr (CL == 2) {
+              // both CTAs load (own A rows + own half of B); all bytes are credited to the leader's full barrier
+              if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+              if constexpr (A_MN) {
 #pragma unroll
-              for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
-            } else {
-              tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
-            }
-            if constexpr (CL > 1) {  // my share of the B tile, multicast to every CTA of the cluster
-              if constexpr (B_MN) {
-                constexpr int kPer = (BLOCK_N / 64) / CL;
-#pragma unroll
-                for (int i = 0; i < kPer; ++i) {
-                  const int a = cta_rank * kPer + i;
-                  tma_load_2d_mc(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0, kMcMask);
-                }
+                for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_2sm(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
               } else {
-                constexpr int kRows = BLOCK_N / CL;
-                tma_load_2d_mc(sb + cta_rank * (kRows * 128), bmap, &full_bar[stage], k0, n0 + cta_rank * kRows, kMcMask);
+                tma_load_2d_2sm(sa, &p.tmap_a, &full_bar[stage], k0, m0);
               }
-            } else if constexpr (B_MN) {
+              const int nh = n0 + cta_rank * (BLOCK_N / 2);
+              if constexpr (B_MN) {
 #pragma unroll
-              for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0);
+                for (int a = 0; a < BLOCK_N / 128; ++a) tma_load_2d_2sm(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], nh + a * 64, k0);
+              } else {
+                tma_load_2d_2sm(sb, bmap, &full_bar[stage], k0, nh);
+              }
             } else {
-              tma_load_2d(sb, bmap, &full_bar[stage], k0, n0);
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              if constexpr (A_MN) {
+#pragma unroll
+                for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &p.tmap_a, &full_bar[stage], m0 + a * 64, k0);
+              } else {
+                tma_load_2d(sa, &p.tmap_a, &full_bar[stage], k0, m0);
+              }
+              if constexpr (B_MN) {
+#pragma unroll
+                for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), bmap, &full_bar[stage], n0 + a * 64, k0);
+              } else {
+                tma_load_2d(sb, bmap, &full_bar[stage], k0, n0);
+              }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == kNStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
     // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 64-element atoms along MN are
     // BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
     constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
     constexpr uint32_t a_kadv = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;  // descriptor start-address units (16 B)
     constexpr uint32_t b_kadv = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int w = cluster_id; w < total_work; w += num_clusters) {
+    for (int w = cluster_id; is_leader && w < total_work; w += num_clusters) {  // 2-SM: only the leader issues
       const int sp = w / (p.tiles_n * tiles_mg);
       const int kb0 = sp * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -208,20 +229,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+          const uint32_t sa = smem_u32(smem_ab + stage * kStgBytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            if constexpr (CL == 2) umma_f16_2sm(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], kMcMask);  // the stage is free once EVERY CTA consumed it
-          else umma_commit(&empty_bar[stage]);
-          if (ki == nk - 1) umma_commit(&tmem_full_bar[acc]);
+          if constexpr (CL == 2) {
+            umma_commit_2sm_mc(&empty_bar[stage], kMcMask);  // releases the stage in BOTH CTAs
+            if (ki == nk - 1) umma_commit_2sm_mc(&tmem_full_bar[acc], kMcMask);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (ki == nk - 1) umma_commit(&tmem_full_bar[acc]);
+          }
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kNStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -229,7 +255,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     // ===================== persist warp (fused broadcast -> GEMM) =====================
     // When B is pulled from a PEER window, the CTA that owns the first M-tile of each N-tile TMA-stores every B stage
     // to the local weight copy while the MMA consumes it: the broadcast rides on the first forward GEMM.
-    if (p.persist_b && lane == 0) {
+    if (CL == 1 && p.persist_b && lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int n_t = w % p.tiles_n;
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           if (last) {  // this warp has drained its share of the accumulator -> hand the TMEM stage back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) { if constexpr (CL == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
           }
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(bar_id, 128);
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           if (last) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) { if constexpr (CL == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
           }
           if (has_aux) {
             mbar_wait(aux_bar, aux_phase);
@@ -422,7 +448,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   if constexpr (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into its shared memory
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

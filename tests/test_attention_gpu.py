@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,T,H,Hkv", [(4, 64, 2, 2), (2, 128, 3, 3), (2, 256, 2, 2), (1, 512, 4, 2), (3, 192, 2, 1),
-                                       (5, 64, 12, 12), (1, 1024, 2, 2), (3, 96, 2, 2)])
+                                       (5, 64, 12, 12), (1, 1024, 2, 2), (3, 96, 2, 2), (2, 64, 4, 2), (3, 32, 2, 2)])
 def test_attention_fwd_bwd(B, T, H, Hkv):
     torch.manual_seed(0)
     hd = 64
