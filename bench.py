@@ -135,7 +135,7 @@ def run_ours(args) -> dict:
     dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
     host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
     val = SyntheticTokens(B, T, V, seed=7, device=str(device), pool=2)
-    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps if args.impl != "nccl" else 0,
+    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps,
                                 val_batches=[b["input_ids"] for b in val.pool], post_pull_lr=5e-5)
     # the optimizer keeps lr=5e-4 in round 0 and 5e-5 after the first pull, as in the reference miner
 
@@ -155,6 +155,7 @@ def run_ours(args) -> dict:
     # ---- warm-up (includes graph capture and one averaging round) ----
     g = run_steps(max(W, 3), dev_data.pool, 0, force_round=True)
     barrier_sync(device)
+    coord.timer.summary()  # drop the warm-up round's phase events
 
     # ---- region 1: device-resident inputs ----
     sampler = ClockSampler(device.index)
@@ -169,6 +170,7 @@ def run_ours(args) -> dict:
     barrier_sync(device)
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1), device)
+    phases = coord.timer.summary()
     rounds = coord.round - rounds0
     eager_launches = ops.launch_count() - c0
     launches = K * trainer.launches_per_step + (eager_launches if trainer.use_graph else eager_launches - K * trainer.launches_per_step)
@@ -186,6 +188,7 @@ def run_ours(args) -> dict:
                    "optimizer": "fused AdamW (fp32 master, bf16 compute)", "cuda_graph": bool(trainer.use_graph),
                    "l2_policy": "per-step working set (weights 0.25 GB bf16 + 1.5 GB fp32 state + ~5 GB activations) >> 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
+        "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},
     }
     # ---- region 2: end to end through the public API (pinned-host inputs, per-step loss read-back) ----
     if not args.no_e2e:

@@ -6,6 +6,7 @@
 // (reference hivetrain/training_manager.py:380-392).
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -497,6 +498,30 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fp8 (e4m3) per-tensor quantisation with DELAYED scaling: q = sat(x / scale_in); amax_out = max|x| (for the next step)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quant_fp8_kernel(const bf16* __restrict__ x, uint8_t* __restrict__ q,
+                                                        const float* __restrict__ scale_in, float* __restrict__ amax_out,
+                                                        size_t n8) {
+  const float inv = 1.f / fmaxf(*scale_in, 1e-12f);
+  float amax = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    float a[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), a);
+    uint2 o;
+    uint8_t* b = reinterpret_cast<uint8_t*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      amax = fmaxf(amax, fabsf(a[k]));
+      b[k] = __nv_cvt_float_to_fp8(a[k] * inv, __NV_SATFINITE, __NV_E4M3);
+    }
+    reinterpret_cast<uint2*>(q)[i] = o;
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(amax));  // amax >= 0
+}
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -593,5 +618,9 @@ extern "C" int dtb_swiglu_bwd(const void* dout, const void* gu, void* dgu, int M
 extern "C" int dtb_rope(void* qkv, int M, int T, int nheads_rot, int row_stride, int hd, float theta, int inverse, int num_sms,
                         cudaStream_t s) {
   rope_kernel<<<num_sms * 8, 256, 0, s>>>((bf16*)qkv, M, T, nheads_rot, row_stride, hd, log2f(theta), inverse ? -1.f : 1.f);
+  return KCHECK();
+}
+extern "C" int dtb_quant_fp8(const void* x, void* q, const float* scale_in, float* amax_out, size_t n, int num_sms, cudaStream_t s) {
+  quant_fp8_kernel<<<num_sms * 8, 256, 0, s>>>((const bf16*)x, (uint8_t*)q, scale_in, amax_out, n / 8);
   return KCHECK();
 }

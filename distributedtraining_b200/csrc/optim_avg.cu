@@ -317,6 +317,68 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// all-gather-by-PULL fused with the round reset.  After the reduce-scatter launch of gather_avg_kernel every rank holds
+// the new base only for ITS shard of the chunk table (in its window).  This kernel reads each chunk from its owner's
+// window (P2P loads: measured 780 GB/s, vs ~210 GB/s for the push form) and in the same pass writes the local fp32 base,
+// the fp32 master, the bf16 compute copy and clears the Adam moments -- the optimizer re-creation after a base pull
+// (reference hivetrain/training_manager.py:365-378) rides on the all-gather.
+// ------------------------------------------------------------------------------------------------------------------
+struct ShardPullParams {
+  const float* shard_src[kMaxMiners];     // base window of every rank (peer-mapped)
+  const uint32_t* wait_flag[kMaxMiners];  // local flag words: shard owner r has published round wait_value
+  const int64_t* chunk_start;
+  const int32_t* chunk_len;
+  float* base_out;
+  float* master;
+  bf16* p16;
+  float* m;
+  float* v;
+  int* error_flag;
+  int world, num_chunks, chunks_per_rank, reset_moments;
+  uint32_t wait_value;
+};
+
+__global__ void __launch_bounds__(256) shard_pull_reset_kernel(const __grid_constant__ ShardPullParams p) {
+  if (p.wait_value != 0) {
+    if (threadIdx.x < p.world && p.wait_flag[threadIdx.x] != nullptr) {
+      long long spins = 0;
+      while (ld_acquire_sys(p.wait_flag[threadIdx.x]) < p.wait_value) {
+        if (++spins > (1ll << 26)) {
+          *p.error_flag = 1;
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = blockIdx.x; c < p.num_chunks; c += gridDim.x) {
+    const int owner = min(c / p.chunks_per_rank, p.world - 1);
+    const float* src = p.shard_src[owner];
+    const size_t start = size_t(p.chunk_start[c]);
+    const int len = p.chunk_len[c];
+    for (int v4 = threadIdx.x; v4 * 4 < len; v4 += blockDim.x) {
+      const size_t e = start + size_t(v4) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(src + e);
+      *reinterpret_cast<float4*>(p.base_out + e) = x;
+      *reinterpret_cast<float4*>(p.master + e) = x;
+      if (p.p16) {
+        uint2 o;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p.p16 + e) = o;
+      }
+      if (p.reset_moments) {
+        *reinterpret_cast<float4*>(p.m + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.v + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // segmented multi-dot (meta-gradient).  Stage 1: per chunk partial sums [num_chunks, N+1]; stage 2: per tensor reduce.
 // ------------------------------------------------------------------------------------------------------------------
@@ -562,5 +624,23 @@ extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStre
 }
 extern "C" int dtb_wait_flags(const uint32_t* flags, int n, int stride, uint32_t value, int* error_flag, cudaStream_t s) {
   wait_flags_kernel<<<1, 64, 0, s>>>(flags, n, stride, value, error_flag);
+  return KCHECK();
+}
+
+extern "C" int dtb_shard_pull_reset(const float** shard_src, const uint32_t** wait_flags, uint32_t wait_value,
+                                    const int64_t* chunk_start, const int32_t* chunk_len, int num_chunks, int chunks_per_rank,
+                                    int world, float* base_out, float* master, void* p16, float* m, float* v, int reset_moments,
+                                    int* error_flag, int grid, cudaStream_t s) {
+  if (world > kMaxMiners) return 3;
+  ShardPullParams p{};
+  for (int r = 0; r < world; ++r) {
+    p.shard_src[r] = shard_src[r];
+    p.wait_flag[r] = wait_flags ? wait_flags[r] : nullptr;
+  }
+  p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.base_out = base_out; p.master = master; p.p16 = (bf16*)p16;
+  p.m = m; p.v = v; p.error_flag = error_flag; p.world = world; p.num_chunks = num_chunks; p.chunks_per_rank = chunks_per_rank;
+  p.reset_moments = reset_moments; p.wait_value = wait_flags ? wait_value : 0;
+  if (grid > num_chunks) grid = num_chunks;
+  shard_pull_reset_kernel<<<grid, 256, 0, s>>>(p);
   return KCHECK();
 }

@@ -54,6 +54,10 @@ struct GemmParams {
   CUtensorMap tmap_b2;  // optional second B operand: C = A (B + B2)^T computed as two accumulating MMA passes
   CUtensorMap tmap_bp;  // optional local destination: B tiles pulled from a peer are persisted here as a side effect
   int dual_b, persist_b;
+  const float* scale_a;  // optional device scalars: effective alpha = alpha * (*scale_a) * (*scale_b)  (fp8 de-quantisation)
+  const float* scale_b;
+  int fp8;      // operands are e4m3 bytes (K-major both): 128 K-elements per stage, tcgen05.mma kind::f8f6f4 (K = 32)
+  int kblk;     // K elements per pipeline stage: 64 (bf16) or 128 (fp8) -- one 128-byte swizzle atom either way
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, num_kb;
   int epi;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem_ab + stage * kStgBytes;
             uint8_t* sb = sa + kABytes;
-            const int k0 = kb * BLOCK_K;
+            const int k0 = kb * p.kblk;
             if constexpr (CL == 2) {
               // both CTAs load (own A rows + own half of B); all bytes are credited to the leader's full barrier
               if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
@@ -210,7 +214,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
+    const uint32_t idesc = p.fp8 ? make_idesc(kFmtE4M3, kFmtE4M3, false, false, BLOCK_M * CL, BLOCK_N)
+                                 : make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
+    const bool fp8 = p.fp8 != 0;
     // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 64-element atoms along MN are
     // BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
     constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
@@ -235,8 +241,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if constexpr (CL == 2) umma_f16_2sm(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
-            else umma_f16(tmem_d, da + uint64_t(k * a_kadv), db + uint64_t(k * b_kadv), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            const uint32_t accf = (ki > 0 || k > 0) ? 1u : 0u;
+            const uint64_t dak = da + uint64_t(k * a_kadv), dbk = db + uint64_t(k * b_kadv);
+            if constexpr (CL == 2) {
+              if (fp8) umma_f8_2sm(tmem_d, dak, dbk, idesc, accf); else umma_f16_2sm(tmem_d, dak, dbk, idesc, accf);
+            } else {
+              if (fp8) umma_f8(tmem_d, dak, dbk, idesc, accf); else umma_f16(tmem_d, dak, dbk, idesc, accf);
+            }
           }
           if constexpr (CL == 2) {
             umma_commit_2sm_mc(&empty_bar[stage], kMcMask);  // releases the stage in BOTH CTAs
@@ -299,6 +310,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     uint8_t* buf = smem_slab + grp * kSlabBytes;
     uint64_t* aux_bar = tmem_empty_bar + 2 + grp;    // after tmem_empty[2]
     uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    const float alpha_eff = p.alpha * (p.scale_a ? (*p.scale_a) * (*p.scale_b) : 1.f);
     constexpr int kColsPerSlab = OUT_F32 ? 32 : 64;
     constexpr int kSlabs = BLOCK_N / kColsPerSlab;
     const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
@@ -339,10 +351,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float4 v;
-            v.x = __uint_as_float(r[ch * 4 + 0]) * p.alpha;
-            v.y = __uint_as_float(r[ch * 4 + 1]) * p.alpha;
-            v.z = __uint_as_float(r[ch * 4 + 2]) * p.alpha;
-            v.w = __uint_as_float(r[ch * 4 + 3]) * p.alpha;
+            v.x = __uint_as_float(r[ch * 4 + 0]) * alpha_eff;
+            v.y = __uint_as_float(r[ch * 4 + 1]) * alpha_eff;
+            v.z = __uint_as_float(r[ch * 4 + 2]) * alpha_eff;
+            v.w = __uint_as_float(r[ch * 4 + 3]) * alpha_eff;
             *reinterpret_cast<float4*>(rowp + ((ch ^ (row_l & 7)) << 4)) = v;
           }
           fence_proxy_async_smem();
@@ -379,7 +391,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           for (int ch = 0; ch < 8; ++ch) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch * 8 + i]) * p.alpha;
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch * 8 + i]) * alpha_eff;
             if (has_bias) {
               const float4 b0 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8 + 4);
@@ -529,11 +541,13 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
 
 // C ABI.  A: K-major => [M, K] pitch lda; MN-major => [K, M] pitch lda.  B likewise with N.  C: [M, N] pitch ldc.
 // out_f32 => C is fp32 and the tile is reduce-ADDED into it (caller zeroes C); splits > 1 requires out_f32.
-extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
-                             int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
-                             float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,
-                             void* b_persist, int ldbp) {
+static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                     int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
+                     float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2, void* b_persist,
+                     int ldbp, const float* scale_a = nullptr, const float* scale_b = nullptr) {
   using namespace dtb;
+  const int KBLK = 128 / esz;  // K elements per 128-byte swizzle atom
+  if (esz == 1 && (a_mn || b_mn || b2 || b_persist)) return 2002;  // fp8 path: K-major operands only
   GemmParams p;
   int rc = 0;
   const int tiles_m_ = (M + BLOCK_M - 1) / BLOCK_M, tiles_n_ = (N + BLOCK_N - 1) / BLOCK_N;
@@ -541,9 +555,9 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   int CL = (!b2 && !b_persist && tiles_m_ >= 2 && tiles_m_ * tiles_n_ >= 32) ? 2 : 1;
   if (force_cl == 1 || b2 || b_persist) CL = 1;
   if (a_mn) rc |= make_tmap_2d(&p.tmap_a, a, 2, M, K, lda, 64, BLOCK_K);
-  else      rc |= make_tmap_2d(&p.tmap_a, a, 2, K, M, lda, BLOCK_K, BLOCK_M);
+  else      rc |= make_tmap_2d(&p.tmap_a, a, esz, K, M, lda, KBLK, BLOCK_M);
   if (b_mn) rc |= make_tmap_2d(&p.tmap_b, b, 2, N, K, ldb, 64, BLOCK_K);
-  else      rc |= make_tmap_2d(&p.tmap_b, b, 2, K, N, ldb, BLOCK_K, BLOCK_N / CL);
+  else      rc |= make_tmap_2d(&p.tmap_b, b, esz, K, N, ldb, KBLK, BLOCK_N / CL);
   if (out_f32) rc |= make_tmap_2d(&p.tmap_c, c, 4, N, M, ldc, 32, BLOCK_M);
   else         rc |= make_tmap_2d(&p.tmap_c, c, 2, N, M, ldc, 64, BLOCK_M);
   if (c2) rc |= make_tmap_2d(&p.tmap_c2, c2, 2, N, M, ldc2, 64, BLOCK_M);
@@ -567,7 +581,11 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
-  p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb = (K + KBLK - 1) / KBLK;
+  p.kblk = KBLK;
+  p.fp8 = esz == 1;
+  p.scale_a = scale_a;
+  p.scale_b = scale_b;
   if (splits < 1) splits = 1;
   if (!out_f32) splits = 1;
   if (splits > p.num_kb) splits = p.num_kb;
@@ -586,4 +604,19 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
   int grid = nclusters * CL;
   cudaError_t e = CL == 2 ? dispatch<2>(p, grid, a_mn, b_mn, out_f32, stream) : dispatch<1>(p, grid, a_mn, b_mn, out_f32, stream);
   return e == cudaSuccess ? 0 : int(e);
+}
+
+// C ABI.  bf16 operands (all majors / modes) and e4m3 operands (K-major; alpha carries the product of the tensor scales).
+extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                             int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
+                             float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,
+                             void* b_persist, int ldbp) {
+  return gemm_impl(2, a, b, c, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_f32, epi, bias, aux, ldaux, c2, ldc2, alpha, splits, num_sms,
+                   stream, b2, ldb2, b_persist, ldbp);
+}
+extern "C" int dtb_gemm_fp8(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int epi,
+                            const void* bias, const void* aux, int ldaux, void* c2, int ldc2, float alpha, int num_sms,
+                            cudaStream_t stream, const float* scale_a, const float* scale_b) {
+  return gemm_impl(1, a, b, c, M, N, K, lda, ldb, ldc, 0, 0, 0, epi, bias, aux, ldaux, c2, ldc2, alpha, 1, num_sms, stream, nullptr, 0,
+                   nullptr, 0, scale_a, scale_b);
 }

@@ -19,7 +19,7 @@ from .transformer import ModelConfig, TransformerEngine, build_manifest, get_con
 class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
-                 lm_chunk: int = 8192, init_flat: Optional[torch.Tensor] = None):
+                 lm_chunk: int = 8192, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False):
         self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
         self.man: Manifest = build_manifest(self.cfg)
         self.device = torch.device(device)
@@ -41,10 +41,12 @@ class Trainer:
         else:
             self.p16 = self.master  # CPU: compute directly on the fp32 master
         self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
-        self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk)
+        self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk,
+                                        fp8_forward=fp8_forward and self.is_cuda)
         self.use_graph = self.is_cuda if use_graph is None else (use_graph and self.is_cuda)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._eval_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._lg_graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.steps_done = 0
         self.tokens_per_step = batch * seq
@@ -53,6 +55,7 @@ class Trainer:
     def _step_body(self) -> torch.Tensor:
         loss = self.engine.forward_backward()
         ops.adamw_step(self.master, self.p16 if self.is_cuda else None, self.grad, self.m, self.v, self.opt)
+        self.engine.roll_fp8_scales()
         return loss
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -96,7 +99,19 @@ class Trainer:
         if isinstance(input_ids, dict):
             input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
         self.engine.set_batch(input_ids, labels)
-        return self.engine.forward_backward(zero_grad)
+        if not (self.use_graph and zero_grad and self.engine.n_rows == self.batch):
+            return self.engine.forward_backward(zero_grad)
+        if self._lg_graph is None:  # same capture protocol as step(): eager warm-up on a side stream, then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.engine.forward_backward(True)
+            torch.cuda.current_stream().wait_stream(s)
+            self._lg_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._lg_graph):
+                self.engine.forward_backward(True)
+        self._lg_graph.replay()
+        return self.engine.loss
 
     @torch.no_grad()
     def eval_loss(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -249,7 +249,7 @@ class TransformerEngine:
     """Static-buffer forward/backward.  ``params`` is the compute-dtype arena (bf16 on GPU), ``grads`` the fp32 arena."""
 
     def __init__(self, cfg: ModelConfig, manifest: Manifest, params: torch.Tensor, grads: Optional[torch.Tensor],
-                 batch: int, seq: int, lm_chunk: int = 8192):
+                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False):
         self.cfg, self.man = cfg, manifest
         self.B, self.T, self.M = batch, seq, batch * seq
         assert seq <= cfg.n_positions
@@ -259,6 +259,7 @@ class TransformerEngine:
         self.P_flat = params
         self._delta = self._src = None
         self._src_flat = None
+        self._w8_stale = True
         self.G = ModelParams(cfg, manifest, grads) if grads is not None else None
         self.grads = grads
         d, Fd, M = cfg.n_embd, cfg.ffn_dim, self.M
@@ -295,6 +296,23 @@ class TransformerEngine:
         self.datt = mk(M, cfg.n_head * cfg.head_dim)
         self.du = mk(M, 2 * Fd if glu else Fd)
         self.dact = mk(M, Fd) if glu else None
+        # ---- optional fp8 (e4m3) forward GEMMs with delayed per-tensor scaling (BASELINE.json config 4: "fp8 miners") ----
+        # forward GEMM operands are quantised (weights once per step, activations by a one-pass quantise kernel that also
+        # collects the amax for the NEXT step); backward GEMMs stay bf16.  All scales live in two device vectors.
+        self.fp8 = bool(fp8_forward)
+        if self.fp8:
+            n_sc = 8 * L + 2
+            self._scales = torch.full((n_sc,), 8.0 / 448.0, dtype=f32, device=self.dev)
+            self._amaxes = torch.zeros(n_sc, dtype=f32, device=self.dev)
+
+            def sc(i):
+                st = ops.Fp8Scale.__new__(ops.Fp8Scale)
+                st.scale, st.amax = self._scales[i:i + 1], self._amaxes[i:i + 1]
+                return st
+            self._sc = [sc(i) for i in range(n_sc)]
+            self.w8 = torch.zeros(manifest.total, dtype=torch.uint8, device=self.dev)
+            self.P8 = ModelParams(cfg, manifest, self.w8)
+            self.a8 = torch.empty(M * max(Fd, d, cfg.n_head * cfg.head_dim), dtype=torch.uint8, device=self.dev)
         self.targets = torch.full((batch, seq), -1, dtype=torch.int32, device=self.dev)
         self.ids = torch.zeros((batch, seq), dtype=torch.int32, device=self.dev)
         self.n_rows = batch
@@ -348,6 +366,31 @@ class TransformerEngine:
             self._small_ids = torch.nonzero(small[ct.long()]).flatten().to(torch.int32)
         return self._small_ids
 
+    _FP8_SLOTS = {"qkv_w": 0, "o_w": 1, "fc_w": 2, "proj_w": 3}
+
+    def _fgemm(self, l: Optional[int], name: str, a, out, **kw):
+        """Forward GEMM ``out = epi(a @ W^T)``: bf16 tcgen05 path, or e4m3 operands when ``fp8_forward`` is on."""
+        if not self.fp8 or self._delta is not None or self._src is not None:
+            g = self._w(l, name)
+            return ops.gemm(a, g.pop("b"), out, **g, **kw)
+        L = self.cfg.n_layer
+        slot = 8 * l + 2 * self._FP8_SLOTS[name] if l is not None else 8 * L
+        sa, sw = self._sc[slot], self._sc[slot + 1]
+        w = getattr(self.P.layers[l], name) if l is not None else self.P.wte
+        w8 = getattr(self.P8.layers[l], name) if l is not None else self.P8.wte
+        if self._w8_stale:
+            ops.quantize_fp8(w, w8, sw)
+        a8 = self.a8[:a.numel()].view(a.shape)
+        ops.quantize_fp8(a, a8, sa)
+        return ops.gemm_fp8(a8, w8, out, sa, sw, **kw)
+
+    def roll_fp8_scales(self) -> None:
+        """Delayed scaling: scale <- amax / 448 for the next step (3 vectorised device ops for all tensors)."""
+        if self.fp8:
+            torch.clamp(self._amaxes, min=1e-8, out=self._scales)
+            self._scales.mul_(1.0 / 448.0)
+            self._amaxes.zero_()
+
     def _w(self, l: Optional[int], name: str) -> dict:
         """kwargs (b, b2, b_persist) of the weight operand ``name`` of layer ``l`` (None = model level)."""
         pick = (lambda P: getattr(P.layers[l], name)) if l is not None else (lambda P: getattr(P, name))
@@ -360,6 +403,7 @@ class TransformerEngine:
 
     def forward(self, train: bool = True) -> None:
         cfg = self.cfg
+        self._w8_stale = True  # weights may have changed since the last forward: re-quantise them on first use
         delta, src = getattr(self, "_delta", None), getattr(self, "_src", None)
         P = src if src is not None else self.P  # small tensors (norms, biases, embeddings) are read where the weights are
         B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
@@ -368,24 +412,20 @@ class TransformerEngine:
         for l, Lp in enumerate(P.layers):
             x = self.xs[l]
             self._norm_fwd(x, Lp.ln1_w, Lp.ln1_b, self.h1[l], self.mean1[l], self.rstd1[l])
-            g = self._w(l, "qkv_w")
-            ops.gemm(self.h1[l], g.pop("b"), self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b, **g)
+            self._fgemm(l, "qkv_w", self.h1[l], self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b)
             if cfg.family == "llama":
                 ops.rope_(self.qkv[l], B, T, H, Hkv, hd, cfg.rope_theta)
             ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv)
-            g = self._w(l, "o_w")
-            ops.gemm(self.att[l], g.pop("b"), self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
-                     aux=x, **g)
+            self._fgemm(l, "o_w", self.att[l], self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
+                        aux=x)
             self._norm_fwd(self.xmid[l], Lp.ln2_w, Lp.ln2_b, self.h2[l], self.mean2[l], self.rstd2[l])
-            g = self._w(l, "fc_w")
             if cfg.family == "gpt2":
-                ops.gemm(self.h2[l], g.pop("b"), self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l], **g)
+                self._fgemm(l, "fc_w", self.h2[l], self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l])
             else:
-                ops.gemm(self.h2[l], g.pop("b"), self.u[l], **g)
+                self._fgemm(l, "fc_w", self.h2[l], self.u[l])
                 ops.swiglu_fwd(self.u[l], self.act[l])
-            g = self._w(l, "proj_w")
-            ops.gemm(self.act[l], g.pop("b"), self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
-                     bias=Lp.proj_b, aux=self.xmid[l], **g)
+            self._fgemm(l, "proj_w", self.act[l], self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
+                        bias=Lp.proj_b, aux=self.xmid[l])
         self._norm_fwd(self.xs[-1], P.lnf_w, P.lnf_b, self.xf, self.meanf, self.rstdf)
 
     def _lm_head(self, backward: bool) -> None:

@@ -88,6 +88,52 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     return out
 
 
+class Fp8Scale:
+    """Delayed per-tensor scaling state for one fp8 (e4m3) tensor: ``scale`` is used THIS step, ``amax`` is collected for
+    the next one (``roll()`` once per step: scale <- max(amax, tiny) / 448, amax <- 0).  All on the device."""
+
+    E4M3_MAX = 448.0
+
+    def __init__(self, device, init_scale: float = 1.0 / 448.0 * 8.0):
+        self.scale = torch.full((1,), init_scale, dtype=torch.float32, device=device)
+        self.amax = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def roll(self) -> None:
+        torch.maximum(self.amax, torch.full_like(self.amax, 1e-8), out=self.scale)
+        self.scale.mul_(1.0 / self.E4M3_MAX)
+        self.amax.zero_()
+
+
+def quantize_fp8(x, q, st: "Fp8Scale"):
+    """q (uint8 storage of e4m3) = sat(x / st.scale); st.amax = max(st.amax, max|x|).  One pass."""
+    if not use_kernels(x):
+        st.amax.copy_(torch.maximum(st.amax, x.float().abs().max().reshape(1)))
+        q.view(torch.float8_e4m3fn).copy_((x.float() / st.scale).clamp(-448, 448).to(torch.float8_e4m3fn))
+        return q
+    _c(_lib.lib().dtb_quant_fp8(_lib.ptr(x), _lib.ptr(q), _lib.ptr(st.scale), _lib.ptr(st.amax), ctypes.c_size_t(x.numel()),
+                                _lib.num_sms(), _lib.stream_ptr()), "quant_fp8")
+    _tick()
+    return q
+
+
+def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=None, aux=None, out2=None):
+    """out[M,N] (bf16) = epi(sa*sb * A8 @ B8^T) with e4m3 operands (K-major), fp32 accumulation on kind::f8f6f4 tensor cores."""
+    if not use_kernels(out):
+        A = a8.view(torch.float8_e4m3fn).float() * sa.scale
+        B = b8.view(torch.float8_e4m3fn).float() * sb.scale
+        return ref.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2)
+    M, K = a8.shape
+    N = b8.shape[0]
+    assert b8.shape[1] == K and out.dtype == torch.bfloat16 and K % 16 == 0
+    rc = _lib.lib().dtb_gemm_fp8(_lib.ptr(a8), _lib.ptr(b8), _lib.ptr(out), M, N, K, a8.stride(0), b8.stride(0), out.stride(0),
+                                 EPI[epi], _lib.ptr(bias), _lib.ptr(aux), _row_major(aux, "aux") if aux is not None else 0,
+                                 _lib.ptr(out2), _row_major(out2, "out2") if out2 is not None else 0, ctypes.c_float(1.0),
+                                 _lib.num_sms(), _lib.stream_ptr(), _lib.ptr(sa.scale), _lib.ptr(sb.scale))
+    _c(rc, "gemm_fp8")
+    _tick()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # embedding / norms / activations / loss
 # ---------------------------------------------------------------------------------------------------------------------
@@ -423,3 +469,19 @@ def multi_dot(g, deltas, base, avg, manifest, out, *, dscales=None, mode=None):
     _c(rc, "multi_dot")
     _tick(2)
     return out
+
+
+def shard_pull_reset(shard_ptrs, manifest, chunks_per_rank, base_out, master, p16, m, v, *, reset_moments=True, wait_flags=None,
+                     wait_value=0, error_flag=None):
+    """All-gather-by-pull fused with the round reset: chunk c is read from ``shard_ptrs[c // chunks_per_rank]`` (peer-mapped
+    base windows) and written to base_out / master / p16 (bf16) with the Adam moments cleared.  csrc/optim_avg.cu."""
+    assert use_kernels(master), "shard_pull_reset is a peer-memory op (CUDA only)"
+    cs, cl, _ = manifest.seg_table(master.device)
+    world = len(shard_ptrs)
+    rc = _lib.lib().dtb_shard_pull_reset(
+        _ptr_array([_dp(x) for x in shard_ptrs]), _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None,
+        ctypes.c_uint32(wait_value), _lib.ptr(cs), _lib.ptr(cl), cs.numel(), chunks_per_rank, world, _lib.ptr(base_out),
+        _lib.ptr(master), _lib.ptr(p16), _lib.ptr(m), _lib.ptr(v), int(reset_moments), _lib.ptr(error_flag),
+        _lib.num_sms() * 8, _lib.stream_ptr())
+    _c(rc, "shard_pull_reset")
+    _tick()

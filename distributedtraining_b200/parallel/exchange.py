@@ -284,6 +284,33 @@ class PeerExchange(Exchange):
         self.win.wait(self.F_BASE, self._base_round)
         return self.win.local("base", torch.float32)[:self.man.total]
 
+    def reduce_scatter_average(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int]) -> int:
+        """Phase 1 of the pull-only round: this rank reduces ITS shard of the arena from all miners' windows (P2P loads)
+        into its own base window and publishes the base flag.  Returns chunks_per_rank."""
+        cs, _, _ = self.man.seg_table(base.device)
+        nchunks = cs.numel()
+        per = (nchunks + self.world - 1) // self.world
+        c0, c1 = min(nchunks, self.rank * per), min(nchunks, (self.rank + 1) * per)
+        d, s = self._delta_ptrs(round, miners)
+        wf = [self.win.flag_ptr(self.F_DELTA + r) for r in miners]
+        self.nan_flags.zero_()
+        mode = {"fp32": 0, "bf16": 1, "fp8": 2}[self.delta_dtype_name]
+        ops.weighted_avg(base, d, w, self.man, [self.win.ptr("base", self.rank)], None, dscales=s, nan_flags=self.nan_flags,
+                         wait_flags=wf, wait_value=round, error_flag=self.win.error_flag, chunk_range=(c0, c1), mode=mode)
+        self._base_round = round + 1
+        self.win.publish(self.F_BASE, self._base_round)
+        return per
+
+    def all_gather_reset(self, trainer, chunks_per_rank: int, reset_moments: bool = True) -> None:
+        """Phase 2: pull every shard from its owner's window, fused with the optimizer/base reset of ``trainer``."""
+        src = [self.win.ptr("base", r) for r in range(self.world)]
+        wf = [self.win.flag_ptr(self.F_BASE + r) for r in range(self.world)]
+        ops.shard_pull_reset(src, self.man, chunks_per_rank, trainer.base, trainer.master, trainer.p16 if trainer.is_cuda else None,
+                             trainer.m, trainer.v, reset_moments=reset_moments, wait_flags=wf, wait_value=self._base_round,
+                             error_flag=self.win.error_flag)
+        # nobody may overwrite a shard (next round's phase 1) before every rank has pulled it
+        self.win.device_barrier()
+
     def publish_base(self, base: torch.Tensor, round: int, dst_ranks: Optional[List[int]] = None) -> None:
         """Averager -> everyone: P2P stores of the fp32 base (+bf16 copy) into each rank's landing window, then flag."""
         dst = list(range(self.world)) if dst_ranks is None else dst_ranks

@@ -23,6 +23,7 @@ import torch.distributed as dist
 
 from .. import ops
 from ..utils.logging import logger
+from ..utils.tracing import PhaseTimer
 from .exchange import CollectiveExchange, PeerExchange
 
 
@@ -39,6 +40,8 @@ class LocalSGDCoordinator:
         self.mixer, self.meta_steps, self.meta_lr = mixer, meta_steps, meta_lr
         self.val_batches = val_batches or []
         self.post_pull_lr, self.reset_optimizer = post_pull_lr, reset_optimizer
+        self.timer = PhaseTimer(enabled=True)  # CUDA-event phase timers (read once, at the end of a bench)
+        self.pull_only = True  # measured: P2P loads reach ~780 GB/s, P2P stores ~210 GB/s -> both halves of the round pull
         self.round = 0
         N, P = len(self.miners), len(trainer.man)
         dev = trainer.master.device
@@ -60,6 +63,21 @@ class LocalSGDCoordinator:
                           mode={"fp32": 0, "bf16": 1, "fp8": 2}[ex.delta_dtype_name])
             self.w.add_(self._G, alpha=-self.meta_lr)
 
+    def _meta_learn_collective(self) -> None:
+        """Same learned-mixer steps on the collective (NCCL/gloo) plane: deltas come from an all_gather, w is broadcast."""
+        t, ex = self.trainer, self.ex
+        g = ex.allgather_deltas(t)
+        if self.rank == self.averager_rank:
+            deltas = [g[i] for i in range(g.shape[0])]
+            for k in range(self.meta_steps):
+                batch = self.val_batches[(self.round * self.meta_steps + k) % len(self.val_batches)]
+                ops.weighted_avg(t.base, deltas, self.w, t.man, [t.master], [t.p16] if t.is_cuda else None)
+                t.loss_and_grad(batch)
+                ops.multi_dot(t.grad, deltas, t.base, t.master, t.man, self._G)
+                self.w.add_(self._G, alpha=-self.meta_lr)
+        if dist.is_initialized():
+            dist.broadcast(self.w, src=self.averager_rank)
+
     def _share_w_peer(self) -> None:
         """Averager -> all: the mixing matrix travels through the windows (a few KB), flag-synchronised."""
         from .symm import F_HEART
@@ -80,13 +98,28 @@ class LocalSGDCoordinator:
         self.round += 1
         r = self.round
         if isinstance(self.ex, PeerExchange):
-            self.ex.publish_delta(t, r)
+            with self.timer.phase("delta_emit"):
+                self.ex.publish_delta(t, r)
             if self.mixer == "learned" and self.meta_steps > 0 and self.val_batches:
-                if self.rank == self.averager_rank:
-                    self._meta_learn_peer(r)
-                self._share_w_peer()
+                with self.timer.phase("meta_learning"):
+                    if self.rank == self.averager_rank:
+                        self._meta_learn_peer(r)
+                    self._share_w_peer()
+            if self.pull_only and getattr(t, "is_cuda", False) and hasattr(t, "engine"):
+                # reduce-scatter by pull, then all-gather by pull fused with the base/optimizer reset (2 kernels, no pushes)
+                with self.timer.phase("gather_avg"):
+                    per = self.ex.reduce_scatter_average(t.base, self.w, r, self.miners)
+                with self.timer.phase("broadcast_reset"):
+                    self.ex.all_gather_reset(t, per, reset_moments=self.reset_optimizer)
+                if self.reset_optimizer:
+                    t.opt.reset()
+                if self.post_pull_lr is not None:
+                    t.opt.set_lr(self.post_pull_lr)
+                return
             new_base = self.ex.sharded_average_broadcast(t.base, self.w, r, self.miners)
         elif isinstance(self.ex, CollectiveExchange):
+            if self.mixer == "learned" and self.meta_steps > 0 and self.val_batches:
+                self._meta_learn_collective()
             # baseline plane: NCCL/gloo all_gather + torch weighted sum (every rank computes the full average)
             self.ex.allgather_average(t, self.w, self._new_base)
             new_base = self._new_base

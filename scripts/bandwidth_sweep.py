@@ -16,8 +16,13 @@ NVLINK_GBS = 770.0  # measured peer-copy bandwidth per direction per GPU (B200_P
 
 
 class T:
+    is_cuda = True
+
     def __init__(self, master, base):
         self.master, self.base = master, base
+        self.p16 = torch.empty(master.numel(), dtype=torch.bfloat16, device=master.device)
+        self.m = torch.zeros_like(master)
+        self.v = torch.zeros_like(master)
     def emit_delta(self, out, scales=None):
         return ops.delta_emit(self.master, self.base, out, scales)
 
@@ -58,6 +63,11 @@ def main():
             st["r"] += 1
             ex.win.publish(ex.F_DELTA, st["r"])          # delta already resident: time the exchange + reduction only
             ex.sharded_average_broadcast(base, w, st["r"], miners)
+        def fused_pull_round():  # reduce-scatter by pull + all-gather by pull fused with the base/optimizer reset
+            st["r"] += 1
+            ex.win.publish(ex.F_DELTA, st["r"])
+            per = ex.reduce_scatter_average(base, w, st["r"], miners)
+            ex.all_gather_reset(tr, per)
         pull_out = torch.empty(n, device=dev)
         def fused_pull():
             st["r"] += 1
@@ -75,19 +85,27 @@ def main():
             _torch_weighted_avg(base, allg, w, tid, ref)
         def nccl_allgather_only():
             dist.all_gather_into_tensor(allg.view(-1), mine)
+        base0 = base.clone()
+        t_pr = timed(fused_pull_round, dev)
+        base.copy_(base0)  # the pull round adopts the new base in place; restore for the other variants
         t_sh, t_pull = timed(fused_sharded, dev), timed(fused_pull, dev)
         t_nf, t_ag = timed(nccl_full, dev), timed(nccl_allgather_only, dev)
         torch.cuda.synchronize(); ex.win.check_errors()
         bytes_delta = n * esz
         in_sharded = (world - 1) * bytes_delta / world      # per-rank NVLink ingress of the sharded kernel
         row = {"delta_mb_fp32": mb, "delta_bytes": bytes_delta,
-               "ms_fused_sharded_gather_avg_bcast": t_sh, "ms_fused_pull_gather_avg_rank0": t_pull,
+               "ms_fused_pull_round_rs_plus_ag_reset": t_pr, "ms_fused_sharded_gather_avg_bcast": t_sh, "ms_fused_pull_gather_avg_rank0": t_pull,
                "ms_nccl_allgather_plus_torch_avg": t_nf, "ms_nccl_allgather_only": t_ag,
                "fused_sharded_ingress_gbs_per_rank": in_sharded / t_sh / 1e6 if world > 1 else None,
                "fused_pull_ingress_gbs_rank0": (world - 1) * bytes_delta / t_pull / 1e6 if world > 1 else None,
                "nccl_allgather_busbw_gbs": (world - 1) * n * mine.element_size() / t_ag / 1e6 if world > 1 else None,
                "roofline_ms_sharded": max(in_sharded / (NVLINK_GBS * 1e6), (world + 2) * n * 4 / world / (6578.7 * 1e6)),
-               "speedup_vs_nccl_path": t_nf / t_sh}
+               "speedup_vs_nccl_path": t_nf / min(t_sh, t_pr)}
+        # pull round: NVLink ingress = 2 x (world-1)/world x bytes (delta shards in phase 1 at esz, fp32 base shards in phase 2)
+        in_pull = (world - 1) / world * (bytes_delta + n * 4)
+        row["pull_round_ingress_gbs_per_rank"] = in_pull / t_pr / 1e6 if world > 1 else None
+        row["roofline_ms_pull_round"] = max(in_pull / (NVLINK_GBS * 1e6), 22.0 * n / (6578.7 * 1e6))
+        row["fraction_of_roofline_pull_round"] = row["roofline_ms_pull_round"] / t_pr
         row["fraction_of_roofline"] = row["roofline_ms_sharded"] / t_sh
         out["rows"].append(row)
         if rank == 0:

@@ -54,6 +54,19 @@ def main():
         if rank == 0:
             ex.gather_average(base, w, r, list(range(world)), pull)
         got = ex.sharded_average_broadcast(base, w, r, list(range(world))).clone()
+        # pull-only round: reduce-scatter by pull + all-gather by pull fused with the reset
+        class PT:
+            is_cuda = True
+        pt = PT()
+        pt.base, pt.master = base.clone(), torch.zeros(n, device=dev)
+        pt.p16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        pt.m, pt.v = torch.ones(n, device=dev), torch.ones(n, device=dev)
+        per = ex.reduce_scatter_average(pt.base, w, r, list(range(world)))
+        ex.all_gather_reset(pt, per)
+        torch.cuda.synchronize()
+        err_pr = max((pt.base - ref).abs().max().item(), (pt.master - ref).abs().max().item())
+        err_pr16 = (pt.p16.float() - ref).abs().max().item()
+        moments_cleared = bool(pt.m.abs().max().item() == 0 and pt.v.abs().max().item() == 0)
         torch.cuda.synchronize()
         ex.win.check_errors()
         err_sh = (got - ref).abs().max().item()
@@ -84,11 +97,13 @@ def main():
         t_ours = timed(ours)
         t_nccl = timed(nccl) if dt == "fp32" else None
         esz = {"fp32": 4, "bf16": 2, "fp8": 1}[dt]
-        res = {"dtype": dt, "max_err_sharded": err_sh, "max_err_pull": err_pull, "max_err_bf16_copy": err_b16, "ref_max": scale,
+        res = {"dtype": dt, "max_err_pull_round": err_pr, "max_err_pull_round_bf16": err_pr16, "moments_cleared": moments_cleared,
+               "max_err_sharded": err_sh, "max_err_pull": err_pull, "max_err_bf16_copy": err_b16, "ref_max": scale,
                "ms_fused_round": t_ours, "ms_nccl_allgather_torch_avg": t_nccl,
                "delta_bytes": n * esz, "nvlink_in_bytes_per_rank": (world - 1) * n * esz // world}
         tol = {"fp32": 1e-5, "bf16": 1e-5, "fp8": 1e-5}[dt] * max(scale, 1.0)
-        res["ok"] = bool(err_sh <= tol and err_pull <= tol and err_b16 <= 1e-2 * max(scale, 1.0))
+        res["ok"] = bool(err_sh <= tol and err_pull <= tol and err_b16 <= 1e-2 * max(scale, 1.0) and err_pr <= tol
+                         and err_pr16 <= 1e-2 * max(scale, 1.0) and moments_cleared)
         out["results"].append(res)
         ex.win.close()
     allok = torch.tensor([int(all(r["ok"] for r in out["results"]))], device=dev)

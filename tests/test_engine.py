@@ -145,3 +145,16 @@ def test_fused_delta_and_peer_source_forward(name):
     for sp in man:  # every tensor arrived as a side effect of the first forward (arena padding is not transported)
         assert torch.allclose(man.view(local, sp.name), man.view(base + delta, sp.name)), sp.name
     assert abs(float(eng3.forward_loss()) - want) < 1e-5
+
+
+@pytest.mark.gpu
+def test_fp8_forward_trains_close_to_bf16():
+    """fp8 (e4m3, delayed scaling) forward GEMMs: losses track the bf16 engine and the model still learns."""
+    torch.manual_seed(0)
+    ids = [torch.randint(0, 512, (8, 64), dtype=torch.int32, device="cuda") for _ in range(4)]
+    res = {}
+    for fp8 in (False, True):
+        tr = Trainer("gpt2-tiny", device="cuda", batch=8, seq=64, lr=1e-3, seed=1, use_graph=False, fp8_forward=fp8)
+        res[fp8] = [float(tr.step(ids[i % 4])) for i in range(12)]
+    assert res[True][-1] < res[True][0]
+    assert max(abs(a - b) for a, b in zip(res[False], res[True])) < 0.15, (res[False], res[True])

@@ -284,3 +284,29 @@ def test_gemm_dual_b_and_persist():
     dst2 = torch.zeros_like(Bt)
     ops.gemm(A, Bt, out, b_mn=True, b_persist=dst2)
     assert torch.equal(dst2, Bt)
+
+
+def test_gemm_fp8_delayed_scaling():
+    """e4m3 x e4m3 GEMM (kind::f8f6f4) with delayed per-tensor scales against the fp32 product of the DEQUANTISED operands
+    (exact up to accumulation order) and against the unquantised product (fp8 rounding error)."""
+    torch.manual_seed(12)
+    M, N, K = 1024, 768, 1536
+    A, B = _bf(M, K, scale=0.7), _bf(N, K, scale=0.05)
+    sa, sb = ops.Fp8Scale(DEV), ops.Fp8Scale(DEV)
+    a8, b8 = torch.empty(M, K, device=DEV, dtype=torch.uint8), torch.empty(N, K, device=DEV, dtype=torch.uint8)
+    for _ in range(2):  # step 0 collects amax with the initial scale, step 1 uses the rolled scale
+        ops.quantize_fp8(A, a8, sa)
+        ops.quantize_fp8(B, b8, sb)
+        assert abs(sa.amax.item() - A.float().abs().max().item()) < 1e-6
+        sa.roll(); sb.roll()
+    ops.quantize_fp8(A, a8, sa)
+    ops.quantize_fp8(B, b8, sb)
+    bias = _bf(N)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_fp8(a8, b8, out, sa, sb, epi="bias", bias=bias)
+    Ad = a8.view(torch.float8_e4m3fn).float() * sa.scale
+    Bd = b8.view(torch.float8_e4m3fn).float() * sb.scale
+    _close(out, Ad @ Bd.t() + bias.float(), rtol=1e-2)
+    exact = A.float() @ B.float().t() + bias.float()
+    rel = (out.float() - exact).norm() / exact.norm()
+    assert rel < 6e-2, float(rel)
