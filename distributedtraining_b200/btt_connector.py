@@ -387,3 +387,37 @@ def rank_network(config, rank: int, world: int, store=None, validator_ranks: Ite
     BittensorNetwork.initialize(config, ignore_regs=True, ledger=StoreLedger(store) if store is not None else MemoryLedger(),
                                 hotkeys=hotkeys, stakes=stakes)
     return BittensorNetwork
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# module-level helpers kept for API parity (reference btt_connector.py:19-63, 99-260)
+# ---------------------------------------------------------------------------------------------------------------------
+def initialize_bittensor_objects(config, ignore_regs: bool = True, ledger=None):
+    """(wallet, ledger, metagraph) -- the reference's version refers to undefined Mock* classes under ``--mock``; here
+    ``--mock`` simply selects the in-memory ledger."""
+    BittensorNetwork.initialize(config, ignore_regs=ignore_regs, ledger=ledger or MemoryLedger())
+    return BittensorNetwork.wallet, BittensorNetwork.ledger, BittensorNetwork.metagraph
+
+
+def resync_metagraph(lite: bool = True) -> None:
+    BittensorNetwork.resync_metagraph(lite)
+
+
+def sync(lite: bool = True) -> None:
+    BittensorNetwork.sync(lite)
+
+
+def serve_extrinsic(ledger, wallet, ip: str, port: int, netuid: int = 1, protocol: int = 4) -> bool:
+    """Advertise this neuron's endpoint (the reference copies bittensor's axon-serve extrinsic; nothing calls it)."""
+    try:
+        ledger.put(f"axon/{netuid}/{wallet.hotkey_str}", json.dumps({"ip": ip, "port": port, "protocol": protocol,
+                                                                      "block": current_block()}))
+        return True
+    except Exception as e:
+        logger.warning(f"serve_extrinsic failed: {e}")
+        return False
+
+
+def serve_axon(netuid: int, host_address: str, external_address: str, host_port: int, external_port: int) -> bool:
+    return serve_extrinsic(BittensorNetwork.ledger, BittensorNetwork.wallet, external_address or host_address, external_port or host_port,
+                           netuid)

@@ -215,56 +215,68 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
   }
 }
 
-// Fast path (d = VPL * 256): per-lane column partials for dw/db stay in REGISTERS across all rows of the warp and are
-// flushed once per warp (shared-memory atomics) and once per block (global atomics).
+// Fast path (d = VPL * 256).  Column partials (dw, db, colsum of dresid) are accumulated in WARP-PRIVATE shared-memory rows
+// with plain read-modify-writes (each lane owns fixed columns, each warp its own row -> no atomics, no register
+// accumulators), which keeps the kernel at <= 128 registers / two CTAs per SM; the first version held 72 accumulators in
+// registers (226 regs, 12 % occupancy, 41 us for 16384 x 768 -- 2.7x off the bandwidth bound, profiles/ncu_misc_v1.json).
 template <bool RMS, int VPL, bool COL>
-__global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const bf16* __restrict__ w, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, const bf16* __restrict__ dresid,
-                                                            bf16* __restrict__ dx, float* __restrict__ dw,
-                                                            float* __restrict__ db, int M, float* __restrict__ dcol) {
+__global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                               const bf16* __restrict__ w, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const bf16* __restrict__ dresid,
+                                                               bf16* __restrict__ dx, float* __restrict__ dw,
+                                                               float* __restrict__ db, int M, float* __restrict__ dcol) {
   constexpr int d = VPL * 256;
-  extern __shared__ float sm[];  // [3][d]: dw | db | column sums of dresid (bias grad of the producing GEMM)
-  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+  constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
+  extern __shared__ float sm[];  // [8 warps][NACC][d]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  float ww[VPL][8], adw[VPL][8], adb[VPL][8], adc[COL ? VPL : 1][8];
-#pragma unroll
-  for (int j = 0; j < VPL; ++j) {
-    unpack8(__ldg(reinterpret_cast<const uint4*>(w) + lane + 32 * j), ww[j]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      adw[j][k] = adb[j][k] = 0.f;
-      if (COL) adc[j][k] = 0.f;
-    }
-  }
+  float* my = sm + size_t(wib) * NACC * d;
+  for (int i = lane; i < NACC * d; i += 32) my[i] = 0.f;
+  __syncwarp();
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
   for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
     const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * d);
+    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
     const float mu = RMS ? 0.f : mean[row];
     const float rs = rstd[row];
-    float g[VPL][8], xh[VPL][8];
-    float s1 = 0.f, s2 = 0.f;
-    const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
-    uint4 rq[VPL], gq[VPL], xq[VPL];
+    uint4 gq[VPL], xq[VPL], rq[VPL];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {  // all loads of the row are issued before any use
+    for (int j = 0; j < VPL; ++j) {  // every load of the row is in flight before the first use
       gq[j] = __ldg(dyr + lane + 32 * j);
       xq[j] = __ldg(xr + lane + 32 * j);
       if (rr) rq[j] = __ldg(rr + lane + 32 * j);
     }
+    float g[VPL][8], xh[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
+      float ww[8];
+      unpack8(__ldg(wv + lane + 32 * j), ww);  // L1-resident
       unpack8(gq[j], g[j]);
       unpack8(xq[j], xh[j]);
+      float* acc = my + (lane + 32 * j) * 8;
+      float4 a0 = *reinterpret_cast<float4*>(acc), a1 = *reinterpret_cast<float4*>(acc + 4);
+      float4 b0, b1;
+      if (!RMS) {
+        b0 = *reinterpret_cast<float4*>(acc + d);
+        b1 = *reinterpret_cast<float4*>(acc + d + 4);
+      }
+      float* ap = &a0.x; float* ap1 = &a1.x; float* bp = &b0.x; float* bp1 = &b1.x;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         xh[j][k] = (xh[j][k] - mu) * rs;
-        adw[j][k] += g[j][k] * xh[j][k];
-        if (!RMS) adb[j][k] += g[j][k];
-        g[j][k] *= ww[j][k];
+        const float t = g[j][k] * xh[j][k];
+        if (k < 4) ap[k] += t; else ap1[k - 4] += t;
+        if (!RMS) { if (k < 4) bp[k] += g[j][k]; else bp1[k - 4] += g[j][k]; }
+        g[j][k] *= ww[k];
         s1 += g[j][k];
         s2 += g[j][k] * xh[j][k];
+      }
+      *reinterpret_cast<float4*>(acc) = a0;
+      *reinterpret_cast<float4*>(acc + 4) = a1;
+      if (!RMS) {
+        *reinterpret_cast<float4*>(acc + d) = b0;
+        *reinterpret_cast<float4*>(acc + d + 4) = b1;
       }
     }
     s1 = RMS ? 0.f : warp_sum(s1) * (1.f / d);
@@ -273,32 +285,38 @@ __global__ void __launch_bounds__(256) norm_bwd_fast_kernel(const bf16* __restri
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       float r[8];
-      if (rr) unpack8(rq[j], r);
+      if (rr) {
+        unpack8(rq[j], r);
+        if (COL) {
+          float* acc = my + (NACC - 1) * d + (lane + 32 * j) * 8;
+          float4 c0 = *reinterpret_cast<float4*>(acc), c1 = *reinterpret_cast<float4*>(acc + 4);
+          c0.x += r[0]; c0.y += r[1]; c0.z += r[2]; c0.w += r[3];
+          c1.x += r[4]; c1.y += r[5]; c1.z += r[6]; c1.w += r[7];
+          *reinterpret_cast<float4*>(acc) = c0;
+          *reinterpret_cast<float4*>(acc + 4) = c1;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = (g[j][k] - s1 - xh[j][k] * s2) * rs;
-        if (rr) {
-          v += r[k];
-          if (COL) adc[j][k] += r[k];
-        }
+        if (rr) v += r[k];
         g[j][k] = v;
       }
       o[lane + 32 * j] = pack8(g[j]);
     }
   }
-#pragma unroll
-  for (int j = 0; j < VPL; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&sm[(lane + 32 * j) * 8 + k], adw[j][k]);
-      if (!RMS) atomicAdd(&sm[d + (lane + 32 * j) * 8 + k], adb[j][k]);
-      if (COL) atomicAdd(&sm[2 * d + (lane + 32 * j) * 8 + k], adc[j][k]);
-    }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(&dw[i], sm[i]);
-    if (!RMS && db) atomicAdd(&db[i], sm[d + i]);
-    if (COL && dcol) atomicAdd(&dcol[i], sm[2 * d + i]);
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int wq = 0; wq < wpb; ++wq) {
+      const float* r = sm + size_t(wq) * NACC * d;
+      a += r[i];
+      if (!RMS) b += r[d + i];
+      if (COL) c += r[(NACC - 1) * d + i];
+    }
+    atomicAdd(&dw[i], a);
+    if (!RMS && db) atomicAdd(&db[i], b);
+    if (COL && dcol) atomicAdd(&dcol[i], c);
   }
 }
 
@@ -545,17 +563,27 @@ extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* o
   else norm_fwd_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)out, mean, rstd, M, d, eps);
   return KCHECK();
 }
+template <bool RMS, int VPL, bool COL>
+static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                                  const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
+                                  float* dcol) {
+  constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
+  const size_t smem = size_t(8) * NACC * VPL * 256 * sizeof(float);
+  auto k = norm_bwd_fast_kernel<RMS, VPL, COL>;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cfg = true;
+  }
+  k<<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (const bf16*)dresid, (bf16*)dx, dw, db,
+                            M, dcol);
+}
 template <bool RMS, int VPL>
 static void launch_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                                  const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
                                  float* dcol) {
-  const size_t smem = size_t(3) * VPL * 256 * sizeof(float);
-  if (dcol)
-    norm_bwd_fast_kernel<RMS, VPL, true><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
-                                                                 (const bf16*)dresid, (bf16*)dx, dw, db, M, dcol);
-  else
-    norm_bwd_fast_kernel<RMS, VPL, false><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
-                                                                  (const bf16*)dresid, (bf16*)dx, dw, db, M, nullptr);
+  if (dcol) launch_norm_bwd_fast2<RMS, VPL, true>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);
+  else launch_norm_bwd_fast2<RMS, VPL, false>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, nullptr);
 }
 extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                             const void* dresid, void* dx, float* dw, float* db, int M, int d, int rms, int num_sms,
@@ -563,7 +591,7 @@ extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const 
   // dcol (optional): += column sums of dresid, i.e. the bias gradient of the GEMM that produced the residual branch.
   // Folded into this pass for d = 768 (register budget); otherwise the caller falls back to dtb_colsum.
   if (dcol && !(d == 768 && dresid)) return 7;
-  const int grid = min((M + 7) / 8, num_sms * 2);
+  const int grid = min((M + 7) / 8, num_sms * 4);
 #define FAST(V)                                                                                             \
   if (d == V * 256 && (rms || V < 8)) {                                                                     \
     if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);      \

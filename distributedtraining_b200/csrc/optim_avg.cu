@@ -498,6 +498,29 @@ __global__ void __launch_bounds__(256) multi_dot_stage2(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// device-side model checksum (replaces the reference's sha256 over a 498 MB D2H copy per miner: validation_logic.py:133,
+// 198-203).  64-bit Fletcher-style pair (sum of words, sum of position-weighted words) over the raw fp32 bits; the
+// integer atomics make it order independent, hence deterministic.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) checksum_kernel(const uint32_t* __restrict__ x, size_t n, unsigned long long* out) {
+  unsigned long long a = 0, b = 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const unsigned long long v = x[i];
+    a += v;
+    b += v * ((i & 0xFFFFFull) + 1ull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, a);
+    atomicAdd(out + 1, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // cross-GPU flags
 // ------------------------------------------------------------------------------------------------------------------
 struct FlagParams {
@@ -642,5 +665,11 @@ extern "C" int dtb_shard_pull_reset(const float** shard_src, const uint32_t** wa
   p.reset_moments = reset_moments; p.wait_value = wait_flags ? wait_value : 0;
   if (grid > num_chunks) grid = num_chunks;
   shard_pull_reset_kernel<<<grid, 256, 0, s>>>(p);
+  return KCHECK();
+}
+
+extern "C" int dtb_checksum(const void* x, size_t n_words, unsigned long long* out2, int num_sms, cudaStream_t s) {
+  cudaMemsetAsync(out2, 0, 16, s);
+  checksum_kernel<<<num_sms * 4, 256, 0, s>>>((const uint32_t*)x, n_words, out2);
   return KCHECK();
 }

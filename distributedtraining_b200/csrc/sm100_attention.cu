@@ -712,19 +712,21 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
 
 // backward, all five products in ONE CTA (no recomputation across kernels):
 //   S = Q K^T, dP = dO V^T  ->  P, dS  ->  dV = P^T dO, dK = dS^T Q, dQ = dS K.     (MHA only: H == Hkv)
-// smem: Q K V dO | P(2) | dS(2) = 128 KB; TMEM: S[128] dP[128] dV[64] dK[64] dQ[64] = 448 columns.
-constexpr int kBwdSmallSmem = 1024 + kTile * 8 + 64;
+// smem: Q K dO | V -> P0 | P1 | dS(2) = 112 KB (P overwrites V, which is dead once dP is computed);
+// TMEM: S[128] dP[128], then dV/dK/dQ overwrite them (every thread has consumed S/dP) = 256 columns -> TWO CTAs per SM
+// overlap each other's TMA / MMA / softmax phases (the first version ran one CTA per SM at 6 % occupancy, 126 us/layer).
+constexpr int kBwdSmallSmem = kTile * 7 + 64;
 
-__global__ void __launch_bounds__(128, 1) attn_bwd_small_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;  // the dynamic window starts 1 KB-aligned (no static shared memory in this kernel)
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;
-  uint8_t* sV = smem + 2 * kTile;
-  uint8_t* sDO = smem + 3 * kTile;
-  uint8_t* sP = smem + 4 * kTile;
-  uint8_t* sDS = smem + 6 * kTile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * kTile);
+  uint8_t* sDO = smem + 2 * kTile;
+  uint8_t* sV = smem + 3 * kTile;
+  uint8_t* sP = smem + 3 * kTile;   // aliases V
+  uint8_t* sDS = smem + 5 * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qb = blockIdx.x, h = blockIdx.y;
@@ -740,14 +742,16 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_small_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const uint32_t tS = tmem, tDP = tmem + 128;
+  const uint32_t tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;  // reuse S / dP after the softmax tiles are in smem
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // layout assumption of the swizzled tiles
   const uint32_t lane_off = (uint32_t(warp) * 32u) << 16;
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
   constexpr uint32_t idesc_g = make_idesc(kFmtBF16, kFmtBF16, true, true, 128, 64);
@@ -822,7 +826,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_small_kernel(const __grid_con
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 

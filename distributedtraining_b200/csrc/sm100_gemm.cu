@@ -67,21 +67,29 @@ struct GemmParams {
   float alpha;
 };
 
-DTB_DEVICE float gelu_tanh_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
+// GELU (tanh form, HF "gelu_new") with MUFU.TANH in fp32.  (A packed tanh.approx.bf16x2 variant halves the MUFU count but
+// its bf16-precision tanh is not accurate enough for the derivative: (1 - t^2) amplifies the error -- measured, reverted.)
+DTB_DEVICE float tanh_fast(float u) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.f + t);
+  return t;
 }
-DTB_DEVICE float dgelu_tanh_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float x2 = x * x;
-  float u = k0 * (x + k1 * x * x2);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  float du = k0 * (1.f + 3.f * k1 * x2);
-  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+DTB_DEVICE void gelu_tanh_pair(float& x0, float& x1) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float t0 = tanh_fast(x0 * fmaf(k01, x0 * x0, k0)), t1 = tanh_fast(x1 * fmaf(k01, x1 * x1, k0));
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  x0 = fmaf(h0, t0, h0);
+  x1 = fmaf(h1, t1, h1);
+}
+// d/dx gelu_tanh for a pair: 0.5(1+t) + 0.5 x (1-t^2) k0 (1 + 3 k1 x^2)
+DTB_DEVICE float2 dgelu_tanh_pair(float x0, float x1) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f, k3 = 3.f * 0.7978845608028654f * 0.044715f;
+  const float s0 = x0 * x0, s1 = x1 * x1;
+  const float t0 = tanh_fast(x0 * fmaf(k01, s0, k0)), t1 = tanh_fast(x1 * fmaf(k01, s1, k0));
+  float2 r;
+  r.x = fmaf(0.5f * x0 * fmaf(-t0, t0, 1.f), fmaf(k3, s0, k0), fmaf(0.5f, t0, 0.5f));
+  r.y = fmaf(0.5f * x1 * fmaf(-t1, t1, 1.f), fmaf(k3, s1, k0), fmaf(0.5f, t1, 0.5f));
+  return r;
 }
 DTB_DEVICE uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -409,7 +417,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
               f = unpack_bf16x2(q.w); a[6] = f.x; a[7] = f.y;
               if (p.epi == EPI_DGELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= dgelu_tanh_f(a[i]);
+                for (int i = 0; i < 8; i += 2) {
+                  const float2 g = dgelu_tanh_pair(a[i], a[i + 1]);
+                  v[i] *= g.x;
+                  v[i + 1] *= g.y;
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += a[i];
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             *reinterpret_cast<uint4*>(rowp + sw) = o;
             if (dual) {  // keep gelu(u) in registers (re-packed into r) for the second store
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_f(v[i]);
+              for (int i = 0; i < 8; i += 2) gelu_tanh_pair(v[i], v[i + 1]);
               r[ch * 4 + 0] = pack_bf16x2(v[0], v[1]); r[ch * 4 + 1] = pack_bf16x2(v[2], v[3]);
               r[ch * 4 + 2] = pack_bf16x2(v[4], v[5]); r[ch * 4 + 3] = pack_bf16x2(v[6], v[7]);
             }

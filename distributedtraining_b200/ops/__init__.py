@@ -485,3 +485,22 @@ def shard_pull_reset(shard_ptrs, manifest, chunks_per_rank, base_out, master, p1
         _lib.num_sms() * 8, _lib.stream_ptr())
     _c(rc, "shard_pull_reset")
     _tick()
+
+
+def checksum(flat: torch.Tensor) -> str:
+    """Order-independent 128-bit device checksum of a flat fp32/bf16 arena (hex string).  CPU: same arithmetic in torch."""
+    words = flat.contiguous().view(torch.int32)
+    n = words.numel()
+    if use_kernels(flat):
+        out = torch.zeros(2, dtype=torch.int64, device=flat.device)
+        _c(_lib.lib().dtb_checksum(_lib.ptr(words), ctypes.c_size_t(n), _lib.ptr(out), _lib.num_sms(), _lib.stream_ptr()), "checksum")
+        _tick()
+        a, b = [int(v) & 0xFFFFFFFFFFFFFFFF for v in out.tolist()]
+    else:
+        v = words.to(torch.int64) & 0xFFFFFFFF
+        idx = (torch.arange(n, dtype=torch.int64) & 0xFFFFF) + 1
+        a = int(v.sum().item()) & 0xFFFFFFFFFFFFFFFF
+        b = 0
+        for c0 in range(0, n, 1 << 20):  # python ints avoid int64 overflow of the weighted sum
+            b = (b + int((v[c0:c0 + (1 << 20)] * idx[c0:c0 + (1 << 20)]).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return f"{a:016x}{b:016x}"

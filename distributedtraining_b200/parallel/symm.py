@@ -25,7 +25,8 @@ FLAG_WORDS = FLAG_BYTES // 4
 F_DELTA = 0     # [F_DELTA + src]  = last delta round published by rank src
 F_BASE = 64     # [F_BASE + src]   = last base round pushed by averager-shard src
 F_BARRIER = 128  # [F_BARRIER + src] = barrier epoch
-F_HEART = 192   # [F_HEART + src]  = heartbeat counter
+F_HEART = 192   # [F_HEART + src]  = averager's mixing-matrix epoch (w broadcast)
+F_ALIVE = 256   # [F_ALIVE + src]  = liveness heartbeat counter (failure detection)
 
 
 class _CudaBuffer:
@@ -139,6 +140,18 @@ class SymmetricWindow:
         self._epoch += 1
         self.publish(F_BARRIER, self._epoch)
         self.wait(F_BARRIER, self._epoch)
+
+    # -- failure detection ---------------------------------------------------------------------------------------------
+    def heartbeat(self) -> None:
+        """Bump this rank's liveness counter in every peer's flag page (stream-ordered, one tiny kernel)."""
+        self._beat = getattr(self, "_beat", 0) + 1
+        self.publish(F_ALIVE, self._beat)
+
+    def stale_ranks(self, min_beat: int) -> List[int]:
+        """Ranks whose heartbeat counter is below ``min_beat`` (host read of the local flag page): a dead or stalled
+        miner is then treated exactly like a failed download in the reference -- skipped for the round."""
+        f = self.flags()[F_ALIVE:F_ALIVE + self.world].tolist()
+        return [r for r, v in enumerate(f) if r != self.rank and v < min_beat]
 
     def check_errors(self) -> None:
         if int(self.error_flag.item()) != 0:

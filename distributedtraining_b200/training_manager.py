@@ -229,6 +229,17 @@ class LocalTrainingLoop:
     """Mixin: store deltas/gradients in a local directory instead of pushing (reference :326-342)."""
 
     @staticmethod
+    def store_gradients(aggregated_gradients, local_dir: str, gradient_file_name: str = "gradients.pt") -> str:
+        """Reference signature (training_manager.py:327-342): save a name->tensor dict (or a flat tensor) locally."""
+        if isinstance(aggregated_gradients, dict):
+            return LocalTrainingLoop.store_gradients_to_dir(aggregated_gradients, local_dir, gradient_file_name)
+        os.makedirs(local_dir, exist_ok=True)
+        path = os.path.join(local_dir, gradient_file_name)
+        torch.save(aggregated_gradients.detach().cpu(), path + ".tmp")
+        os.replace(path + ".tmp", path)
+        return path
+
+    @staticmethod
     def store_gradients_to_dir(tensors: Dict[str, torch.Tensor], local_dir: str, gradient_file_name: str = "gradients.pt") -> str:
         os.makedirs(local_dir, exist_ok=True)
         path = os.path.join(local_dir, gradient_file_name)
@@ -331,6 +342,11 @@ class MNISTDeltaTrain(LocalTrainingLoop):
                 if max_steps is not None and step >= max_steps:
                     return losses
         return losses
+
+
+class MNISTDeltaTrainHugging(MNISTDeltaTrain):
+    """Reference :171-323 is a near-duplicate of MNISTDeltaTrain that subclasses TrainingLoop with a broken
+    ``super().__init__()``; kept as a working alias."""
 
 
 class TrainingLoopNew(DeltaLoop):

@@ -310,3 +310,13 @@ def test_gemm_fp8_delayed_scaling():
     exact = A.float() @ B.float().t() + bias.float()
     rel = (out.float() - exact).norm() / exact.norm()
     assert rel < 6e-2, float(rel)
+
+
+def test_checksum_matches_cpu_and_detects_change():
+    torch.manual_seed(13)
+    x = torch.randn(256 * 37, device=DEV)
+    c_gpu, c_cpu = ops.checksum(x), ops.checksum(x.cpu())
+    assert c_gpu == c_cpu and len(c_gpu) == 32
+    y = x.clone()
+    y[1234] += 1e-3
+    assert ops.checksum(y) != c_gpu
