@@ -64,6 +64,8 @@ struct GemmParams {
   int ldaux;
   const __nv_bfloat16* bias;  // [N]
   const __nv_bfloat16* aux;   // [M, ldaux]
+  __nv_bfloat16* c2;          // second output (pre-activation), written with direct 16 B stores in the dual epilogue
+  int ldc2;
   float alpha;
 };
 
@@ -107,7 +109,10 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
 //         ring deepens to 6 stages.  Only the pair's leader issues MMAs; TMA bytes of both CTAs are credited to the
 //         leader's full barrier; stage release / accumulator-ready are multicast commits; the non-leader's epilogue
 //         arrives remotely on the leader's TMEM-empty barrier.
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL>
+// FP8: e4m3 operands (K-major only), kind::f8f6f4.  A TEMPLATE parameter on purpose: a runtime branch in the single-thread
+// MMA issue loop cost 20 % of the GEMM throughput (measured: 1088 -> 860 TFLOP/s on 16384x2304x768) -- the issuing thread has
+// ~128 cycles per instruction and every extra branch/select in that loop starves the tensor pipe.
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem_ab + stage * kStgBytes;
             uint8_t* sb = sa + kABytes;
-            const int k0 = kb * p.kblk;
+            const int k0 = kb * (FP8 ? 128 : BLOCK_K);
             if constexpr (CL == 2) {
               // both CTAs load (own A rows + own half of B); all bytes are credited to the leader's full barrier
               if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
@@ -222,9 +227,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = p.fp8 ? make_idesc(kFmtE4M3, kFmtE4M3, false, false, BLOCK_M * CL, BLOCK_N)
-                                 : make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
-    const bool fp8 = p.fp8 != 0;
+    constexpr uint32_t idesc = FP8 ? make_idesc(kFmtE4M3, kFmtE4M3, false, false, BLOCK_M * CL, BLOCK_N)
+                                   : make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
     // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 64-element atoms along MN are
     // BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
     constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 16, b_lbo = B_MN ? BLOCK_K * 128 : 16;
@@ -252,9 +256,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             const uint32_t accf = (ki > 0 || k > 0) ? 1u : 0u;
             const uint64_t dak = da + uint64_t(k * a_kadv), dbk = db + uint64_t(k * b_kadv);
             if constexpr (CL == 2) {
-              if (fp8) umma_f8_2sm(tmem_d, dak, dbk, idesc, accf); else umma_f16_2sm(tmem_d, dak, dbk, idesc, accf);
+              if constexpr (FP8) umma_f8_2sm(tmem_d, dak, dbk, idesc, accf); else umma_f16_2sm(tmem_d, dak, dbk, idesc, accf);
             } else {
-              if (fp8) umma_f8(tmem_d, dak, dbk, idesc, accf); else umma_f16(tmem_d, dak, dbk, idesc, accf);
+              if constexpr (FP8) umma_f8(tmem_d, dak, dbk, idesc, accf); else umma_f16(tmem_d, dak, dbk, idesc, accf);
             }
           }
           if constexpr (CL == 2) {
@@ -328,6 +332,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       const int n_t = w % p.tiles_n;
       const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
       const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
+      const int row = m0 + int(row_l);
+      const bool row_ok = row < p.M;
       if (has_bias) {
         named_bar_sync(3, kEpiThreads);  // previous tile's readers of smem_bias are done
         for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) {
@@ -432,6 +438,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
             *reinterpret_cast<uint4*>(rowp + sw) = o;
             if (dual) {  // keep gelu(u) in registers (re-packed into r) for the second store
+              // (direct 16 B global stores of u were tried instead of the second TMA round trip: 813 vs 868 TFLOP/s -- kept TMA)
 #pragma unroll
               for (int i = 0; i < 8; i += 2) gelu_tanh_pair(v[i], v[i + 1]);
               r[ch * 4 + 0] = pack_bf16x2(v[0], v[1]); r[ch * 4 + 1] = pack_bf16x2(v[2], v[3]);
@@ -511,9 +518,9 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inn
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL>
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false>
 static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL>;
+  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -537,6 +544,7 @@ static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
 
 template <int CL>
 static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn, bool out_f32, cudaStream_t stream) {
+  if (p.fp8) return launch<false, false, false, CL, true>(p, grid, stream);
   if (out_f32) {
     if (a_mn && b_mn) return launch<true, true, true, CL>(p, grid, stream);
     if (!a_mn && b_mn) return launch<false, true, true, CL>(p, grid, stream);
@@ -596,6 +604,8 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
   p.num_kb = (K + KBLK - 1) / KBLK;
   p.kblk = KBLK;
   p.fp8 = esz == 1;
+  p.c2 = reinterpret_cast<__nv_bfloat16*>(c2);
+  p.ldc2 = ldc2;
   p.scale_a = scale_a;
   p.scale_b = scale_b;
   if (splits < 1) splits = 1;
