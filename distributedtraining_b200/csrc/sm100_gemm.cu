@@ -246,11 +246,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       for (int ki = 0; ki < nk; ++ki) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_ab + stage * kStgBytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+        // The whole warp runs this loop convergently and only the tcgen05 instructions sit under elect.sync: every operand is
+        // then provably warp-uniform and ptxas keeps the descriptors in uniform registers.  (Issuing under a divergent
+        // `if (lane == 0)` made ptxas wrap EVERY UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop; the single
+        // issuing thread has ~128 cycles per instruction, so that overhead directly starved the tensor pipe.)
+        const uint32_t sa = smem_u32(smem_ab + stage * kStgBytes);
+        const uint32_t sb = sa + kABytes;
+        const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
+        const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t accf = (ki > 0 || k > 0) ? 1u : 0u;
@@ -269,7 +273,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             if (ki == nk - 1) umma_commit(&tmem_full_bar[acc]);
           }
         }
-        __syncwarp();
         if (++stage == kNStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
