@@ -617,17 +617,21 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   const uint32_t lane_off = (uint32_t(warp) * 32u) << 16;
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
   constexpr uint32_t idesc_o = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], 3 * kTile);
-    tma_load_2d(sQ, &p.tmap_qkv, &bars[0], h * kHd, q0);
-    tma_load_2d(sK, &p.tmap_qkv, &bars[0], (p.H + hk) * kHd, q0);
-    tma_load_2d(sV, &p.tmap_qkv, &bars[0], (p.H + p.Hkv + hk) * kHd, q0);
+  if (warp == 0) {  // warp-uniform issue: only the instructions themselves sit under elect.sync (see sm100_gemm.cu)
+    if (elect_one()) {
+      mbar_expect_tx(&bars[0], 3 * kTile);
+      tma_load_2d(sQ, &p.tmap_qkv, &bars[0], h * kHd, q0);
+      tma_load_2d(sK, &p.tmap_qkv, &bars[0], (p.H + hk) * kHd, q0);
+      tma_load_2d(sV, &p.tmap_qkv, &bars[0], (p.H + p.Hkv + hk) * kHd, q0);
+    }
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024), dk = make_smem_desc(smem_u32(sK), 16, 1024);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_f16(tmem, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
-    umma_commit(&bars[1]);
+      for (int k = 0; k < 4; ++k) umma_f16(tmem, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
+      umma_commit(&bars[1]);
+    }
   }
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_tok - q0;
   const float sl2 = p.scale * kLog2e;
@@ -670,15 +674,18 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
     tc_fence_after();
+    const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < kBlk / 16; ++k) {
-      const uint64_t dp = make_smem_desc(smem_u32(sP) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
-      const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 2048, kTile, 1024);
-      umma_f16(tmem, dp, dv, idesc_o, k > 0);  // O overwrites S[0:64] (every thread has consumed S)
+      for (int k = 0; k < kBlk / 16; ++k) {
+        const uint64_t dp = make_smem_desc(pbase + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+        const uint64_t dv = make_smem_desc(vbase + k * 2048, kTile, 1024);
+        umma_f16(tmem, dp, dv, idesc_o, k > 0);  // O overwrites S[0:64] (every thread has consumed S)
+      }
+      umma_commit(&bars[2]);
     }
-    umma_commit(&bars[2]);
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();
@@ -756,21 +763,25 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
   constexpr uint32_t idesc_g = make_idesc(kFmtBF16, kFmtBF16, true, true, 128, 64);
   constexpr uint32_t idesc_q = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], 4 * kTile);
-    tma_load_2d(sQ, &p.tmap_qkv, &bars[0], colQ, q0);
-    tma_load_2d(sK, &p.tmap_qkv, &bars[0], colK, q0);
-    tma_load_2d(sV, &p.tmap_qkv, &bars[0], colV, q0);
-    tma_load_2d(sDO, &p.tmap_do, &bars[0], colQ, q0);
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(&bars[0], 4 * kTile);
+      tma_load_2d(sQ, &p.tmap_qkv, &bars[0], colQ, q0);
+      tma_load_2d(sK, &p.tmap_qkv, &bars[0], colK, q0);
+      tma_load_2d(sV, &p.tmap_qkv, &bars[0], colV, q0);
+      tma_load_2d(sDO, &p.tmap_do, &bars[0], colQ, q0);
+    }
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024), dk = make_smem_desc(smem_u32(sK), 16, 1024);
     const uint64_t ddo = make_smem_desc(smem_u32(sDO), 16, 1024), dv = make_smem_desc(smem_u32(sV), 16, 1024);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_f16(tS, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
+      for (int k = 0; k < 4; ++k) umma_f16(tS, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k > 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_f16(tDP, ddo + uint64_t(k * 2), dv + uint64_t(k * 2), idesc_s, k > 0);
-    umma_commit(&bars[1]);
+      for (int k = 0; k < 4; ++k) umma_f16(tDP, ddo + uint64_t(k * 2), dv + uint64_t(k * 2), idesc_s, k > 0);
+      umma_commit(&bars[1]);
+    }
   }
   float Drow, lse_l2;
   load_row_stats(p, row_tok, h, Drow, lse_l2);
@@ -781,8 +792,9 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
     tc_fence_after();
+    if (elect_one()) {
 #pragma unroll
     for (int k = 0; k < kBlk / 16; ++k) {
       umma_f16(tDV, make_smem_desc(smem_u32(sP) + k * 2048, kTile, 1024), make_smem_desc(smem_u32(sDO) + k * 2048, kTile, 1024),
@@ -799,6 +811,7 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
                make_smem_desc(smem_u32(sK) + k * 2048, kTile, 1024), idesc_q, k > 0);
     }
     umma_commit(&bars[2]);
+    }  // elect_one
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();

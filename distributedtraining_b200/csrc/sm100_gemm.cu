@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   const bool is_leader = cta_rank == 0;
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop; only the issue itself is under elect.sync) =====================
+    {
       uint32_t stage = 0, phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int n_t = w % p.tiles_n;
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             uint8_t* sa = smem_ab + stage * kStgBytes;
             uint8_t* sb = sa + kABytes;
             const int k0 = kb * (FP8 ? 128 : BLOCK_K);
+            if (elect_one()) {
             if constexpr (CL == 2) {
               // both CTAs load (own A rows + own half of B); all bytes are credited to the leader's full barrier
               if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
                 tma_load_2d(sb, bmap, &full_bar[stage], k0, n0);
               }
             }
+            }  // elect_one
             if (++stage == kNStages) { stage = 0; phase ^= 1; }
           }
         }
