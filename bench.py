@@ -38,13 +38,14 @@ def parse_args(argv=None):
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl"])
     ap.add_argument("--model", type=str, default="gpt2")
-    ap.add_argument("--batch-size", type=int, default=256, help="sequences per miner per step")
+    ap.add_argument("--batch-size", type=int, default=512, help="sequences per miner per step (both arms use the same default)")
     ap.add_argument("--seq-len", type=int, default=64, help="reference miner sequence length (neurons/miner.py:70)")
     ap.add_argument("--local-steps", type=int, default=100)
     ap.add_argument("--meta-steps", type=int, default=1, help="learned-mixer SGD steps per round on the averager rank")
     ap.add_argument("--delta-dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp8"])
     ap.add_argument("--lr", type=float, default=5e-4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp8-forward", action="store_true", help="e4m3 forward GEMMs with delayed scaling (config 4)")
     return ap.parse_args(argv)
 
 
@@ -124,7 +125,8 @@ def run_ours(args) -> dict:
     assert device.type == "cuda", "bench.py needs a GPU"
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     B, T, K, W = args.batch_size, args.seq_len, args.steps, args.warmup
-    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0)  # same theta_base on every rank
+    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0,  # same theta_base on every rank
+                      fp8_forward=args.fp8_forward)
     V = trainer.cfg.vocab_size
     if args.impl == "nccl":
         ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
@@ -185,7 +187,7 @@ def run_ours(args) -> dict:
         "config": {"model": f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})", "global_batch": B * world,
                    "micro_batch_per_miner": B, "seq_len": T, "parallelism": f"local-sgd dp{world}", "local_steps": args.local_steps,
                    "meta_steps_per_round": coord.meta_steps, "delta_dtype": args.delta_dtype, "exchange": plane,
-                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "cuda_graph": bool(trainer.use_graph),
+                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward), "cuda_graph": bool(trainer.use_graph),
                    "l2_policy": "per-step working set (weights 0.25 GB bf16 + 1.5 GB fp32 state + ~5 GB activations) >> 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},

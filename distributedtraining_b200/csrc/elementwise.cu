@@ -5,6 +5,7 @@
 // Parity: these replace the ATen kernels behind HF GPT-2 in the reference miner/validator/averager hot loops
 // (reference hivetrain/training_manager.py:380-392).
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
@@ -617,7 +618,8 @@ extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const 
 extern "C" int dtb_ce_fwd_bwd(void* logits, const int* targets, float* losses, int M, int V, int ldl, float grad_scale,
                               int write_grad, cudaStream_t s) {
   const size_t smem = size_t((V + 7) / 8) * 16;
-  if (smem <= 110 * 1024) {  // two CTAs per SM keep the load/compute phases of different rows overlapped
+  static const bool nocache = getenv("DTB200_CE_NOCACHE") != nullptr;  // A/B switch: re-read the row from L2 instead of smem
+  if (smem <= 110 * 1024 && !nocache) {  // two CTAs per SM keep the load/compute phases of different rows overlapped
     static size_t configured = 0;
     if (smem > configured) {
       if (cudaFuncSetAttribute(ce_fwd_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return 2;

@@ -19,7 +19,7 @@ from .transformer import ModelConfig, TransformerEngine, build_manifest, get_con
 class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
-                 lm_chunk: int = 8192, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False):
+                 lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False):
         self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
         self.man: Manifest = build_manifest(self.cfg)
         self.device = torch.device(device)
