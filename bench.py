@@ -45,6 +45,7 @@ def parse_args(argv=None):
     ap.add_argument("--delta-dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp8"])
     ap.add_argument("--lr", type=float, default=5e-4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dropout", type=float, default=None, help="train-mode dropout; default = the model preset (GPT-2: 0.1, as in the reference)")
     ap.add_argument("--fp8-forward", action="store_true", help="e4m3 forward GEMMs with delayed scaling (config 4)")
     return ap.parse_args(argv)
 
@@ -126,7 +127,7 @@ def run_ours(args) -> dict:
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     B, T, K, W = args.batch_size, args.seq_len, args.steps, args.warmup
     trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0,  # same theta_base on every rank
-                      fp8_forward=args.fp8_forward)
+                      fp8_forward=args.fp8_forward, dropout=args.dropout)
     V = trainer.cfg.vocab_size
     if args.impl == "nccl":
         ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
@@ -187,7 +188,7 @@ def run_ours(args) -> dict:
         "config": {"model": f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})", "global_batch": B * world,
                    "micro_batch_per_miner": B, "seq_len": T, "parallelism": f"local-sgd dp{world}", "local_steps": args.local_steps,
                    "meta_steps_per_round": coord.meta_steps, "delta_dtype": args.delta_dtype, "exchange": plane,
-                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward), "cuda_graph": bool(trainer.use_graph),
+                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward), "dropout": trainer.cfg.dropout, "cuda_graph": bool(trainer.use_graph),
                    "l2_policy": "per-step working set (weights 0.25 GB bf16 + 1.5 GB fp32 state + ~5 GB activations) >> 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},

@@ -165,6 +165,18 @@ class Wallet:
         return f"Wallet({self.name}, {self.hotkey_str})"
 
 
+class LocalHotkey(SimpleNamespace):
+    """``wallet.hotkey`` stand-in with only ``ss58_address`` (reference btt_connector.py:514-520)."""
+
+    def __init__(self, ss58_address: str = "simulated_hotkey_0"):
+        super().__init__(ss58_address=ss58_address)
+
+
+# names the reference's simulation layer uses (btt_connector.py:514-585); same objects here
+LocalMetagraph = Metagraph
+LocalWallet = Wallet
+
+
 def current_block() -> int:
     return int(time.time() // BLOCK_SECONDS)
 

@@ -37,6 +37,7 @@ def add_b200_args(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--seq_len", type=int, default=64)
     g.add_argument("--local_steps", type=int, default=100, help="optimizer steps per round (replaces send_interval=800 s)")
     g.add_argument("--lr", type=float, default=5e-4)
+    g.add_argument("--dropout", type=float, default=None, help="train-mode embd/attn/resid dropout (default: the model preset; GPT-2 = 0.1)")
     g.add_argument("--post_pull_lr", type=float, default=5e-5)
     g.add_argument("--no_reset_optimizer", action="store_true")
     g.add_argument("--delta_dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp8"])

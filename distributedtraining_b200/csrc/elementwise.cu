@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "dropout.cuh"
+
 namespace dtb {
 
 using bf16 = __nv_bfloat16;
@@ -42,13 +44,26 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
+// apply the dropout multipliers of 8 consecutive elements (4 pair words starting at pair index `pair0`)
+__device__ __forceinline__ void drop8(float* f, uint32_t key, uint32_t pair0, uint32_t thr, float scale) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t w = drop_word(key, pair0 + k);
+    f[2 * k] *= drop_mul_lo(w, thr, scale);
+    f[2 * k + 1] *= drop_mul_hi(w, thr, scale);
+  }
+}
+
+__global__ void rng_advance_kernel(uint32_t* rng) { rng[1] += 1u; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // embedding
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
                                  bf16* __restrict__ out, int M, int T, int d, const bf16* __restrict__ wte2,
-                                 const bf16* __restrict__ wpe2) {
+                                 const bf16* __restrict__ wpe2, const DropArgs drop) {
   const int row = blockIdx.x;
+  const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   const int id = ids[row];
   const int pos = row % T;
   const uint4* w = reinterpret_cast<const uint4*>(wte + size_t(id) * d);
@@ -72,19 +87,22 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __rest
         for (int k = 0; k < 8; ++k) a[k] += b[k];
       }
     }
+    if (drop.thr) drop8(a, dkey, uint32_t(row) * uint32_t(d >> 1) + uint32_t(i) * 4u, drop.thr, drop.scale);
     o[i] = pack8(a);
   }
 }
 
 __global__ void embed_bwd_kernel(const bf16* __restrict__ dx, const int* __restrict__ ids, float* __restrict__ dwte,
-                                 float* __restrict__ dwpe, int M, int T, int d) {
+                                 float* __restrict__ dwpe, int M, int T, int d, const DropArgs drop) {
   const int row = blockIdx.x;
   const int id = ids[row];
   const int pos = row % T;
+  const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   const uint4* g = reinterpret_cast<const uint4*>(dx + size_t(row) * d);
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
     float a[8];
     unpack8(__ldg(g + i), a);
+    if (drop.thr) drop8(a, dkey, uint32_t(row) * uint32_t(d >> 1) + uint32_t(i) * 4u, drop.thr, drop.scale);
     float4* te = reinterpret_cast<float4*>(dwte + size_t(id) * d + i * 8);
     atomicAdd(te, make_float4(a[0], a[1], a[2], a[3]));
     atomicAdd(te + 1, make_float4(a[4], a[5], a[6], a[7]));
@@ -156,8 +174,9 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ w, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const bf16* __restrict__ dresid,
                                                        bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
-                                                       int M, int d) {
+                                                       int M, int d, bf16* __restrict__ dxm, const DropArgs drop) {
   extern __shared__ float sm[];  // [2][d]
+  const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   float* s_dw = sm;
   float* s_db = sm + d;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
@@ -207,6 +226,10 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
         a[k] = v;
       }
       o[i] = pack8(a);
+      if (dxm) {  // masked copy: the dY of the GEMM whose output went through this dropout site
+        drop8(a, dkey, uint32_t(row) * uint32_t(d >> 1) + uint32_t(i) * 4u, drop.thr, drop.scale);
+        reinterpret_cast<uint4*>(dxm + size_t(row) * d)[i] = pack8(a);
+      }
     }
   }
   __syncthreads();
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
   }
 }
 
-// Fast path (d = VPL * 256).  Column partials (dw, db, colsum of dresid) are accumulated in WARP-PRIVATE shared-memory rows
+// Fast path (d = VPL * 256).  Column partials (dw, db, colsum of the [masked] output) are accumulated in WARP-PRIVATE shared-memory rows
 // with plain read-modify-writes (each lane owns fixed columns, each warp its own row -> no atomics, no register
 // accumulators), which keeps the kernel at <= 128 registers / two CTAs per SM; the first version held 72 accumulators in
 // registers (226 regs, 12 % occupancy, 41 us for 16384 x 768 -- 2.7x off the bandwidth bound, profiles/ncu_misc_v1.json).
@@ -225,8 +248,10 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
                                                                const bf16* __restrict__ w, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const bf16* __restrict__ dresid,
                                                                bf16* __restrict__ dx, float* __restrict__ dw,
-                                                               float* __restrict__ db, int M, float* __restrict__ dcol) {
+                                                               float* __restrict__ db, int M, float* __restrict__ dcol,
+                                                               bf16* __restrict__ dxm, const DropArgs drop) {
   constexpr int d = VPL * 256;
+  const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
   extern __shared__ float sm[];  // [8 warps][NACC][d]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -286,17 +311,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       float r[8];
-      if (rr) {
-        unpack8(rq[j], r);
-        if (COL) {
-          float* acc = my + (NACC - 1) * d + (lane + 32 * j) * 8;
-          float4 c0 = *reinterpret_cast<float4*>(acc), c1 = *reinterpret_cast<float4*>(acc + 4);
-          c0.x += r[0]; c0.y += r[1]; c0.z += r[2]; c0.w += r[3];
-          c1.x += r[4]; c1.y += r[5]; c1.z += r[6]; c1.w += r[7];
-          *reinterpret_cast<float4*>(acc) = c0;
-          *reinterpret_cast<float4*>(acc + 4) = c1;
-        }
-      }
+      if (rr) unpack8(rq[j], r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = (g[j][k] - s1 - xh[j][k] * s2) * rs;
@@ -304,6 +319,18 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
         g[j][k] = v;
       }
       o[lane + 32 * j] = pack8(g[j]);
+      if (dxm) {  // masked copy of the output: the dY of the GEMM whose output went through this dropout site
+        drop8(g[j], dkey, uint32_t(row) * uint32_t(d >> 1) + uint32_t(lane + 32 * j) * 4u, drop.thr, drop.scale);
+        reinterpret_cast<uint4*>(dxm + size_t(row) * d)[lane + 32 * j] = pack8(g[j]);
+      }
+      if (COL) {  // column sums of the (masked) output = bias gradient of that GEMM
+        float* acc = my + (NACC - 1) * d + (lane + 32 * j) * 8;
+        float4 c0 = *reinterpret_cast<float4*>(acc), c1 = *reinterpret_cast<float4*>(acc + 4);
+        c0.x += g[j][0]; c0.y += g[j][1]; c0.z += g[j][2]; c0.w += g[j][3];
+        c1.x += g[j][4]; c1.y += g[j][5]; c1.z += g[j][6]; c1.w += g[j][7];
+        *reinterpret_cast<float4*>(acc) = c0;
+        *reinterpret_cast<float4*>(acc + 4) = c1;
+      }
     }
   }
   __syncthreads();
@@ -546,14 +573,27 @@ __global__ void __launch_bounds__(256) quant_fp8_kernel(const bf16* __restrict__
 using namespace dtb;
 #define KCHECK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
-extern "C" int dtb_embed_fwd(const int* ids, const void* wte, const void* wpe, void* out, int M, int T, int d, cudaStream_t s,
-                             const void* wte2, const void* wpe2) {
-  embed_fwd_kernel<<<M, 128, 0, s>>>(ids, (const bf16*)wte, (const bf16*)wpe, (bf16*)out, M, T, d, (const bf16*)wte2,
-                                     (const bf16*)wpe2);
+static DropArgs make_drop(const void* rng, int stream, float p) {
+  DropArgs d;
+  d.rng = (const uint32_t*)rng;
+  d.stream = uint32_t(stream);
+  d.thr = (rng && p > 0.f) ? uint32_t(p * 65536.f + 0.5f) : 0u;
+  d.scale = 1.f / (1.f - p);
+  return d;
+}
+extern "C" int dtb_rng_advance(void* rng, cudaStream_t s) {
+  rng_advance_kernel<<<1, 1, 0, s>>>((uint32_t*)rng);
   return KCHECK();
 }
-extern "C" int dtb_embed_bwd(const void* dx, const int* ids, float* dwte, float* dwpe, int M, int T, int d, cudaStream_t s) {
-  embed_bwd_kernel<<<M, 128, 0, s>>>((const bf16*)dx, ids, dwte, dwpe, M, T, d);
+extern "C" int dtb_embed_fwd(const int* ids, const void* wte, const void* wpe, void* out, int M, int T, int d, cudaStream_t s,
+                             const void* wte2, const void* wpe2, const void* rng, int stream, float p) {
+  embed_fwd_kernel<<<M, 128, 0, s>>>(ids, (const bf16*)wte, (const bf16*)wpe, (bf16*)out, M, T, d, (const bf16*)wte2,
+                                     (const bf16*)wpe2, make_drop(rng, stream, p));
+  return KCHECK();
+}
+extern "C" int dtb_embed_bwd(const void* dx, const int* ids, float* dwte, float* dwpe, int M, int T, int d, cudaStream_t s,
+                             const void* rng, int stream, float p) {
+  embed_bwd_kernel<<<M, 128, 0, s>>>((const bf16*)dx, ids, dwte, dwpe, M, T, d, make_drop(rng, stream, p));
   return KCHECK();
 }
 extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* out, float* mean, float* rstd, int M, int d,
@@ -567,7 +607,7 @@ extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* o
 template <bool RMS, int VPL, bool COL>
 static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                                   const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
-                                  float* dcol) {
+                                  float* dcol, void* dxm, const DropArgs& drop) {
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
   const size_t smem = size_t(8) * NACC * VPL * 256 * sizeof(float);
   auto k = norm_bwd_fast_kernel<RMS, VPL, COL>;
@@ -577,26 +617,29 @@ static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, 
     cfg = true;
   }
   k<<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (const bf16*)dresid, (bf16*)dx, dw, db,
-                            M, dcol);
+                            M, dcol, (bf16*)dxm, drop);
 }
 template <bool RMS, int VPL>
 static void launch_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                                  const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
-                                 float* dcol) {
-  if (dcol) launch_norm_bwd_fast2<RMS, VPL, true>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);
-  else launch_norm_bwd_fast2<RMS, VPL, false>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, nullptr);
+                                 float* dcol, void* dxm, const DropArgs& drop) {
+  if (dcol) launch_norm_bwd_fast2<RMS, VPL, true>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol, dxm, drop);
+  else launch_norm_bwd_fast2<RMS, VPL, false>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, nullptr, dxm, drop);
 }
 extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                             const void* dresid, void* dx, float* dw, float* db, int M, int d, int rms, int num_sms,
-                            cudaStream_t s, float* dcol) {
-  // dcol (optional): += column sums of dresid, i.e. the bias gradient of the GEMM that produced the residual branch.
-  // Folded into this pass for d = 768 (register budget); otherwise the caller falls back to dtb_colsum.
-  if (dcol && !(d == 768 && dresid)) return 7;
+                            cudaStream_t s, float* dcol, void* dxm, const void* rng, int stream, float p) {
+  // dxm (optional): a second, dropout-masked copy of dx -- the dY of the GEMM whose output went through that dropout site.
+  // dcol (optional): += column sums of dxm (of dx when no mask is given), i.e. that GEMM's bias gradient.
+  // The fold is only built for d = 768 (register budget); otherwise the caller falls back to dtb_colsum.
+  if (dcol && d != 768) return 7;
+  const DropArgs drop = make_drop(dxm ? rng : nullptr, stream, p);
+  if (dxm && !drop.thr) return 8;
   const int grid = min((M + 7) / 8, num_sms * 4);
 #define FAST(V)                                                                                             \
   if (d == V * 256 && (rms || V < 8)) {                                                                     \
-    if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);      \
-    else launch_norm_bwd_fast<false, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol);         \
+    if (rms) launch_norm_bwd_fast<true, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol, dxm, drop); \
+    else launch_norm_bwd_fast<false, V>(dy, x, w, mean, rstd, dresid, dx, dw, db, M, grid, s, dcol, dxm, drop); \
     return KCHECK();                                                                                        \
   }
   FAST(3) FAST(4) FAST(8)
@@ -606,12 +649,12 @@ extern "C" int dtb_norm_bwd(const void* dy, const void* x, const void* w, const 
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
     norm_bwd_kernel<true><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, nullptr, rstd,
-                                                  (const bf16*)dresid, (bf16*)dx, dw, nullptr, M, d);
+                                                  (const bf16*)dresid, (bf16*)dx, dw, nullptr, M, d, (bf16*)dxm, drop);
   } else {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
     norm_bwd_kernel<false><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd,
-                                                   (const bf16*)dresid, (bf16*)dx, dw, db, M, d);
+                                                   (const bf16*)dresid, (bf16*)dx, dw, db, M, d, (bf16*)dxm, drop);
   }
   return KCHECK();
 }

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "dropout.cuh"
 #include "sm100_ptx.cuh"
 
 namespace dtb {
@@ -42,7 +43,22 @@ struct AttnParams {
   float* lse;            // [B, H, T]
   int M, T, H, Hkv, ld_out, ld_o;
   float scale;
+  DropArgs drop;  // attention-probability dropout (GPT-2 attn_pdrop): P is masked AFTER the softmax normaliser is formed
 };
+
+// multiply 32 consecutive probabilities (key tokens kg0 .. kg0+31, kg0 even) of one (head, q row) by their dropout factors
+DTB_DEVICE void drop_p32(float* s, uint32_t rowkey, int kg0, uint32_t thr, float scale) {
+  const uint32_t pair0 = uint32_t(kg0) >> 1;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const uint32_t w = drop_word(rowkey, pair0 + (i >> 1));
+    s[i] *= drop_mul_lo(w, thr, scale);
+    s[i + 1] *= drop_mul_hi(w, thr, scale);
+  }
+}
+DTB_DEVICE uint32_t attn_row_key(const AttnParams& p, int h, int row_tok) {
+  return p.drop.thr ? drop_row_key(drop_key(p.drop.rng, p.drop.stream), uint32_t(h) * uint32_t(p.M) + uint32_t(row_tok)) : 0u;
+}
 
 DTB_DEVICE uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -120,6 +136,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
   constexpr uint32_t idesc_o = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
   const float sl2 = p.scale * kLog2e;
+  const uint32_t dthr = p.drop.thr, rowkey = attn_row_key(p, h, row_tok);
   float m_run = -CUDART_INF_F, l_run = 0.f;
   float acc[kHd];
 #pragma unroll
@@ -176,6 +193,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         s[i] = e;
         lsum += e;
       }
+      if (dthr) drop_p32(s, rowkey, k0 + ch * 32, dthr, p.drop.scale);
       uint8_t* atom = sP + (ch >> 1) * kTile;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
@@ -246,18 +264,33 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 //   P and dS are written as bf16 into swizzled smem tiles.
 template <bool WRITE_P>
 DTB_DEVICE void bwd_softmax_tiles(uint32_t tS, uint32_t tDP, uint32_t lane_off, int tid, int c_lo, int c_hi, float sl2,
-                                  float lse_l2, float Drow, float scale, uint8_t* sP, uint8_t* sDS) {
+                                  float lse_l2, float Drow, float scale, uint8_t* sP, uint8_t* sDS, uint32_t rowkey, int k0,
+                                  uint32_t dthr, float dscale) {
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     float s[32], dp[32];
     tmem_ld32(tS + lane_off + ch * 32, s);
     tmem_ld32(tDP + lane_off + ch * 32, dp);
+    if (dthr) {  // dropout on P: dV uses the masked P, dS = P * (mask * dP - D) * scale  (D = rowsum(dO * O) is unchanged)
+      float mk[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = ch * 32 + i;
-      const float pv = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - lse_l2) : 0.f;
-      s[i] = pv;
-      dp[i] = pv * (dp[i] - Drow) * scale;
+      for (int i = 0; i < 32; ++i) mk[i] = 1.f;
+      drop_p32(mk, rowkey, k0 + ch * 32, dthr, dscale);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = ch * 32 + i;
+        const float pv = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - lse_l2) : 0.f;
+        s[i] = pv * mk[i];
+        dp[i] = pv * (dp[i] * mk[i] - Drow) * scale;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = ch * 32 + i;
+        const float pv = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - lse_l2) : 0.f;
+        s[i] = pv;
+        dp[i] = pv * (dp[i] - Drow) * scale;
+      }
     }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -393,7 +426,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kv_kernel(const __grid_consta
     const int c_lo = seq_start - k0, c_hi = (row_tok < p.M) ? row_tok - k0 : -1;
     mbar_wait(bar_s, it & 1);
     tc_fence_after();
-    bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, sP, sDS);
+    bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, sP, sDS, attn_row_key(p, hq, row_tok), k0,
+                            p.drop.thr, p.drop.scale);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -506,6 +540,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
   constexpr uint32_t idesc_q = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);  // dQ = dS K  (B = K, MN-major)
   const float sl2 = p.scale * kLog2e;
+  const uint32_t rowkey = attn_row_key(p, h, row_tok);
   float Drow, lse_l2;
   load_row_stats(p, row_tok, h, Drow, lse_l2);
   mbar_wait(bar_q, 0);
@@ -535,7 +570,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
     const int c_lo = seq_start - k0, c_hi = (row_tok < p.M) ? row_tok - k0 : -1;
     mbar_wait(bar_s, it & 1);
     tc_fence_after();
-    bwd_softmax_tiles<false>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, nullptr, sDS);
+    bwd_softmax_tiles<false>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, nullptr, sDS, rowkey, k0, p.drop.thr,
+                             p.drop.scale);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -635,6 +671,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   }
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_tok - q0;
   const float sl2 = p.scale * kLog2e;
+  const uint32_t rowkey = attn_row_key(p, h, row_tok);
   mbar_wait(&bars[1], 0);
   tc_fence_after();
   float mx = -CUDART_INF_F;
@@ -662,6 +699,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
       sv[i] = e;
       lsum += e;
     }
+    if (p.drop.thr) drop_p32(sv, rowkey, q0 + ch * 32, p.drop.thr, p.drop.scale);
     // all 128 threads finished READING Q/K? they are only read by the tensor core, which completed (bars[1]) -> safe
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -788,7 +826,8 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = (row_tok < p.M) ? row_tok - q0 : -1;
   mbar_wait(&bars[1], 0);
   tc_fence_after();
-  bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, p.scale * kLog2e, lse_l2, Drow, p.scale, sP, sDS);
+  bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, p.scale * kLog2e, lse_l2, Drow, p.scale, sP, sDS,
+                          attn_row_key(p, h, row_tok), q0, p.drop.thr, p.drop.scale);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -847,10 +886,18 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
 
 using namespace dtb;
 
+static void set_drop(AttnParams& p, const void* rng, int stream, float prob) {
+  p.drop.rng = reinterpret_cast<const uint32_t*>(rng);
+  p.drop.stream = uint32_t(stream);
+  p.drop.thr = (rng && prob > 0.f) ? uint32_t(prob * 65536.f + 0.5f) : 0u;
+  p.drop.scale = 1.f / (1.f - prob);
+}
+
 extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int Hkv, int hd, int ld_qkv,
-                                 int ld_out, float scale, cudaStream_t s) {
+                                 int ld_out, float scale, cudaStream_t s, const void* rng, int drop_stream, float drop_p) {
   if (hd != kHd || H % Hkv != 0) return 10;
   AttnParams p{};
+  set_drop(p, rng, drop_stream, drop_p);
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   p.tmap_do = p.tmap_qkv;
@@ -870,9 +917,11 @@ extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
 }
 
 extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, int B, int T,
-                                 int H, int Hkv, int hd, int ld_qkv, int ld_o, float scale, cudaStream_t s) {
+                                 int H, int Hkv, int hd, int ld_qkv, int ld_o, float scale, cudaStream_t s, const void* rng,
+                                 int drop_stream, float drop_p) {
   if (hd != kHd || H % Hkv != 0) return 10;
   AttnParams p{};
+  set_drop(p, rng, drop_stream, drop_p);
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   if (make_tmap_2d(&p.tmap_do, dout, 2, uint64_t(H) * kHd, M, ld_o, 64, kBlk)) return 11;

@@ -22,6 +22,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "dropout.cuh"
 #include "sm100_ptx.cuh"
 
 namespace dtb {
@@ -67,6 +68,7 @@ struct GemmParams {
   __nv_bfloat16* c2;          // second output (pre-activation), written with direct 16 B stores in the dual epilogue
   int ldc2;
   float alpha;
+  DropArgs drop;  // EPI_BIAS_RESID / EPI_RESID: out = aux + dropout(acc [+ bias])  (GPT-2 resid_pdrop)
 };
 
 // GELU (tanh form, HF "gelu_new") with MUFU.TANH in fp32.  (A packed tanh.approx.bf16x2 variant halves the MUFU count but
@@ -333,6 +335,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
     const bool has_aux = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
     const bool dual = (p.epi == EPI_BIAS_GELU);
+    const uint32_t dthr = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID) ? p.drop.thr : 0u;
+    const uint32_t dkey = dthr ? drop_key(p.drop.rng, p.drop.stream) : 0u;
     for (int w = cluster_id; w < total_work; w += num_clusters) {
       const int n_t = w % p.tiles_n;
       const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
@@ -434,6 +438,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
                   v[i + 1] *= g.y;
                 }
               } else {
+                if (dthr) {  // residual-branch dropout: pair index = row * (N / 2) + col / 2 (dropout.cuh)
+                  const uint32_t pair0 = uint32_t(row) * uint32_t(p.N >> 1) + (uint32_t(gcol0 + ch * 8) >> 1);
+#pragma unroll
+                  for (int i = 0; i < 8; i += 2) {
+                    const uint32_t wd = drop_word(dkey, pair0 + (i >> 1));
+                    v[i] *= drop_mul_lo(wd, dthr, p.drop.scale);
+                    v[i + 1] *= drop_mul_hi(wd, dthr, p.drop.scale);
+                  }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += a[i];
               }
@@ -569,7 +582,7 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
 static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                      int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                      float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2, void* b_persist,
-                     int ldbp, const float* scale_a = nullptr, const float* scale_b = nullptr) {
+                     int ldbp, const float* scale_a, const float* scale_b, const void* rng, int drop_stream, float drop_p) {
   using namespace dtb;
   const int KBLK = 128 / esz;  // K elements per 128-byte swizzle atom
   if (esz == 1 && (a_mn || b_mn || b2 || b_persist)) return 2002;  // fp8 path: K-major operands only
@@ -623,6 +636,11 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.ldaux = ldaux;
   p.alpha = alpha;
+  p.drop.rng = reinterpret_cast<const uint32_t*>(rng);
+  p.drop.stream = uint32_t(drop_stream);
+  p.drop.thr = (rng && drop_p > 0.f) ? uint32_t(drop_p * 65536.f + 0.5f) : 0u;
+  p.drop.scale = 1.f / (1.f - drop_p);
+  if (p.drop.thr && ((N & 1) || !(epi == EPI_BIAS_RESID || epi == EPI_RESID))) return 2003;
   const int tiles_mg = (p.tiles_m + CL - 1) / CL;
   int total = tiles_mg * p.tiles_n * p.splits;   // work items per cluster
   int max_clusters = num_sms / CL;
@@ -637,13 +655,14 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
 extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                              int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                              float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,
-                             void* b_persist, int ldbp) {
+                             void* b_persist, int ldbp, const void* rng, int drop_stream, float drop_p) {
   return gemm_impl(2, a, b, c, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_f32, epi, bias, aux, ldaux, c2, ldc2, alpha, splits, num_sms,
-                   stream, b2, ldb2, b_persist, ldbp);
+                   stream, b2, ldb2, b_persist, ldbp, nullptr, nullptr, rng, drop_stream, drop_p);
 }
 extern "C" int dtb_gemm_fp8(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int epi,
                             const void* bias, const void* aux, int ldaux, void* c2, int ldc2, float alpha, int num_sms,
-                            cudaStream_t stream, const float* scale_a, const float* scale_b) {
+                            cudaStream_t stream, const float* scale_a, const float* scale_b, const void* rng, int drop_stream,
+                            float drop_p) {
   return gemm_impl(1, a, b, c, M, N, K, lda, ldb, ldc, 0, 0, 0, epi, bias, aux, ldaux, c2, ldc2, alpha, 1, num_sms, stream, nullptr, 0,
-                   nullptr, 0, scale_a, scale_b);
+                   nullptr, 0, scale_a, scale_b, rng, drop_stream, drop_p);
 }

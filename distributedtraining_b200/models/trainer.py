@@ -19,8 +19,12 @@ from .transformer import ModelConfig, TransformerEngine, build_manifest, get_con
 class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
-                 lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False):
+                 lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
+                 dropout: Optional[float] = None):
         self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
+        if dropout is not None and dropout != self.cfg.dropout:  # override the preset's train-mode dropout (0 disables)
+            import dataclasses
+            self.cfg = dataclasses.replace(self.cfg, dropout=float(dropout))
         self.man: Manifest = build_manifest(self.cfg)
         self.device = torch.device(device)
         self.is_cuda = self.device.type == "cuda"
@@ -42,7 +46,7 @@ class Trainer:
             self.p16 = self.master  # CPU: compute directly on the fp32 master
         self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
         self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk,
-                                        fp8_forward=fp8_forward and self.is_cuda)
+                                        fp8_forward=fp8_forward and self.is_cuda, seed=seed)
         self.use_graph = self.is_cuda if use_graph is None else (use_graph and self.is_cuda)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._eval_graph: Optional[torch.cuda.CUDAGraph] = None

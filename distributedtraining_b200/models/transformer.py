@@ -39,6 +39,9 @@ class ModelConfig:
     eps: float = 1e-5
     rope_theta: float = 500000.0
     name: str = "gpt2"
+    # embd / attn / resid dropout probability in TRAIN mode.  HF GPT-2 ships 0.1 for all three and the reference miner
+    # trains with it on (reference hivetrain/training_manager.py:46 ``model.train()``); Llama configs use 0.
+    dropout: float = 0.0
 
     @property
     def head_dim(self) -> int:
@@ -58,9 +61,9 @@ class ModelConfig:
 
 
 PRESETS: Dict[str, ModelConfig] = {
-    "gpt2": ModelConfig(name="gpt2"),
-    "gpt2-small": ModelConfig(name="gpt2"),
-    "gpt2-medium": ModelConfig(name="gpt2-medium", n_embd=1024, n_layer=24, n_head=16),
+    "gpt2": ModelConfig(name="gpt2", dropout=0.1),
+    "gpt2-small": ModelConfig(name="gpt2", dropout=0.1),
+    "gpt2-medium": ModelConfig(name="gpt2-medium", n_embd=1024, n_layer=24, n_head=16, dropout=0.1),
     "gpt2-tiny": ModelConfig(name="gpt2-tiny", vocab_size=512, n_positions=128, n_embd=128, n_layer=2, n_head=2),
     "llama-3.2-1b": ModelConfig(family="llama", name="llama-3.2-1b", vocab_size=128256, n_positions=131072, n_embd=2048,
                                 n_layer=16, n_head=32, n_kv_head=8, ffn=8192, eps=1e-5, rope_theta=500000.0),
@@ -200,15 +203,28 @@ def make_targets(input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None)
     return tgt
 
 
-def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_ids: torch.Tensor) -> torch.Tensor:
+def drop_stream(site: str, l: int = 0) -> int:
+    """Dropout site -> stream id of the counter-based mask generator (csrc/dropout.cuh)."""
+    return {"embd": 0, "attn": 1 + 3 * l, "resid1": 2 + 3 * l, "resid2": 3 + 3 * l}[site]
+
+
+def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_ids: torch.Tensor,
+                  drop_state=None) -> torch.Tensor:
+    """Plain autograd forward.  ``drop_state`` (the engine's ``rng.state`` AFTER its advance, or a (seed, counter) tuple)
+    turns on train-mode dropout with exactly the masks the kernels generate."""
+    from ..ops import reference as ref
     P = ModelParams(cfg, man, theta)
     B, T = input_ids.shape
     H, Hkv, hd = cfg.n_head, cfg.kv_heads, cfg.head_dim
+    pd = cfg.dropout if drop_state is not None else 0.0
+    dm = lambda site, l=0: ref.drop_mult_2d(drop_state, drop_stream(site, l), pd, B * T, cfg.n_embd, theta.device).view(B, T, -1)
     x = P.wte[input_ids]
     if P.wpe is not None:
         x = x + P.wpe[:T][None]
+    if pd > 0:
+        x = x * dm("embd")
     mask = torch.ones(T, T, dtype=torch.bool, device=theta.device).tril()
-    for L in P.layers:
+    for l, L in enumerate(P.layers):
         h = _norm(cfg, x, L.ln1_w, L.ln1_b)
         qkv = F.linear(h, L.qkv_w, L.qkv_b)
         q, k, v = qkv.split([H * hd, Hkv * hd, Hkv * hd], dim=-1)
@@ -221,9 +237,12 @@ def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_id
             v = v.repeat_interleave(H // Hkv, dim=1)
         s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
         s = s.masked_fill(~mask, float("-inf"))
-        a = torch.softmax(s, dim=-1) @ v
-        a = a.transpose(1, 2).reshape(B, T, H * hd)
-        x = x + F.linear(a, L.o_w, L.o_b)
+        pr = torch.softmax(s, dim=-1)
+        if pd > 0:
+            pr = pr * ref.drop_mult_attn(drop_state, drop_stream("attn", l), pd, B, T, H, theta.device)
+        a = (pr @ v).transpose(1, 2).reshape(B, T, H * hd)
+        y = F.linear(a, L.o_w, L.o_b)
+        x = x + (y * dm("resid1", l) if pd > 0 else y)
         h = _norm(cfg, x, L.ln2_w, L.ln2_b)
         u = F.linear(h, L.fc_w, L.fc_b)
         if cfg.family == "gpt2":
@@ -231,13 +250,14 @@ def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_id
         else:
             g, up = u.chunk(2, dim=-1)
             act = F.silu(g) * up
-        x = x + F.linear(act, L.proj_w, L.proj_b)
+        y = F.linear(act, L.proj_w, L.proj_b)
+        x = x + (y * dm("resid2", l) if pd > 0 else y)
     x = _norm(cfg, x, P.lnf_w, P.lnf_b)
     return F.linear(x, P.wte)
 
 
-def oracle_loss(cfg, man, theta, input_ids, labels=None) -> torch.Tensor:
-    logits = oracle_logits(cfg, man, theta, input_ids)
+def oracle_loss(cfg, man, theta, input_ids, labels=None, drop_state=None) -> torch.Tensor:
+    logits = oracle_logits(cfg, man, theta, input_ids, drop_state)
     tgt = make_targets(input_ids, labels)
     return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), tgt.view(-1).long(), ignore_index=-1)
 
@@ -249,8 +269,12 @@ class TransformerEngine:
     """Static-buffer forward/backward.  ``params`` is the compute-dtype arena (bf16 on GPU), ``grads`` the fp32 arena."""
 
     def __init__(self, cfg: ModelConfig, manifest: Manifest, params: torch.Tensor, grads: Optional[torch.Tensor],
-                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False):
+                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False, seed: int = 0):
         self.cfg, self.man = cfg, manifest
+        assert cfg.dropout == 0.0 or cfg.family == "gpt2", "dropout sites are defined for the GPT-2 family"
+        self.drop_p = float(cfg.dropout)
+        self.rng = ops.DropoutRng(params.device, seed=0x5EED + seed)
+        self._dropping = False
         self.B, self.T, self.M = batch, seq, batch * seq
         assert seq <= cfg.n_positions
         self.dev = params.device
@@ -291,6 +315,8 @@ class TransformerEngine:
         self.dx = mk(M, d)
         self.dx2 = mk(M, d)
         self.dxf = mk(M, d)
+        if self.drop_p > 0.0 and grads is not None:
+            self.dxm, self.dxm2 = mk(M, d), mk(M, d)  # dropout-masked copies of the residual-stream gradient
         self.dh = mk(M, d)
         self.dqkv = mk(M, cfg.qkv_dim)
         self.datt = mk(M, cfg.n_head * cfg.head_dim)
@@ -324,11 +350,14 @@ class TransformerEngine:
         else:
             ops.rmsnorm_fwd(x, w, self.cfg.eps, out, rstd)
 
-    def _norm_bwd(self, dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol=None):
+    def _norm_bwd(self, dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol=None, dxm=None, drop=None):
         if self.cfg.family == "gpt2":
-            ops.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol)
+            ops.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid, dcol, dxm, drop)
         else:
             ops.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
+
+    def _drop(self, site: str, l: int = 0):
+        return ops.Drop(self.rng, drop_stream(site, l), self.drop_p) if self._dropping else None
 
     def set_batch(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
         """Copy a batch into the static id/target buffers (non-blocking when the source is pinned).  A batch with fewer
@@ -407,17 +436,21 @@ class TransformerEngine:
         delta, src = getattr(self, "_delta", None), getattr(self, "_src", None)
         P = src if src is not None else self.P  # small tensors (norms, biases, embeddings) are read where the weights are
         B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
+        self._dropping = bool(train and self.drop_p > 0.0)
+        if self._dropping:
+            self.rng.advance()  # fresh masks every training forward; backward regenerates them from the same counter
         # the position table belongs to the small set (already base+delta in the arena): only the token rows are added here
-        ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0], *((delta.wte, None) if delta is not None else ()))
+        ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0], *((delta.wte, None) if delta is not None else ()),
+                      drop=self._drop("embd"))
         for l, Lp in enumerate(P.layers):
             x = self.xs[l]
             self._norm_fwd(x, Lp.ln1_w, Lp.ln1_b, self.h1[l], self.mean1[l], self.rstd1[l])
             self._fgemm(l, "qkv_w", self.h1[l], self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b)
             if cfg.family == "llama":
                 ops.rope_(self.qkv[l], B, T, H, Hkv, hd, cfg.rope_theta)
-            ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv)
+            ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv, drop=self._drop("attn", l))
             self._fgemm(l, "o_w", self.att[l], self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
-                        aux=x)
+                        aux=x, drop=self._drop("resid1", l))
             self._norm_fwd(self.xmid[l], Lp.ln2_w, Lp.ln2_b, self.h2[l], self.mean2[l], self.rstd2[l])
             if cfg.family == "gpt2":
                 self._fgemm(l, "fc_w", self.h2[l], self.act[l], epi="bias_gelu", bias=Lp.fc_b, out2=self.u[l])
@@ -425,7 +458,7 @@ class TransformerEngine:
                 self._fgemm(l, "fc_w", self.h2[l], self.u[l])
                 ops.swiglu_fwd(self.u[l], self.act[l])
             self._fgemm(l, "proj_w", self.act[l], self.xs[l + 1], epi="bias_resid" if Lp.proj_b is not None else "resid",
-                        bias=Lp.proj_b, aux=self.xmid[l])
+                        bias=Lp.proj_b, aux=self.xmid[l], drop=self._drop("resid2", l))
         self._norm_fwd(self.xs[-1], P.lnf_w, P.lnf_b, self.xf, self.meanf, self.rstdf)
 
     def _lm_head(self, backward: bool) -> None:
@@ -476,38 +509,51 @@ class TransformerEngine:
             self.grads.zero_()
         self.forward(train=True)
         self._lm_head(backward=True)
+        # Residual-stream gradients ping-pong between dx / dx2.  Each norm backward also produces, on the same pass, what
+        # the NEXT GEMM pair in the backward order needs: its dY (a dropout-masked copy when the site is active, the
+        # residual gradient itself otherwise) and that GEMM's bias gradient (column sums of the dY).
+        L = cfg.n_layer
         dx, dx2 = self.dx, self.dx2
-        self._norm_bwd(self.dxf, self.xs[-1], P.lnf_w, self.meanf, self.rstdf, dx, G.lnf_w, G.lnf_b, None)
-        for l in range(cfg.n_layer - 1, -1, -1):
+        dm, dm2 = (self.dxm, self.dxm2) if self._dropping else (None, None)
+        self._norm_bwd(self.dxf, self.xs[-1], P.lnf_w, self.meanf, self.rstdf, dx, G.lnf_w, G.lnf_b, None,
+                       G.layers[L - 1].proj_b, dm, self._drop("resid2", L - 1))
+        for l in range(L - 1, -1, -1):
             Lp, Lg = P.layers[l], G.layers[l]
+            dy = dm if dm is not None else dx
             # ---- MLP block ----
             if cfg.family == "gpt2":
-                ops.gemm(dx, Lp.proj_w, self.du, b_mn=True, epi="dgelu", aux=self.u[l])
+                ops.gemm(dy, Lp.proj_w, self.du, b_mn=True, epi="dgelu", aux=self.u[l])
             else:
-                ops.gemm(dx, Lp.proj_w, self.dact, b_mn=True)
+                ops.gemm(dy, Lp.proj_w, self.dact, b_mn=True)
                 ops.swiglu_bwd(self.dact, self.u[l], self.du)
-            ops.gemm(dx, self.act[l], Lg.proj_w, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dy, self.act[l], Lg.proj_w, a_mn=True, b_mn=True, accumulate=True)
             ops.gemm(self.du, Lp.fc_w, self.dh, b_mn=True)
             ops.gemm(self.du, self.h2[l], Lg.fc_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.fc_b is not None:
                 ops.colsum(self.du, Lg.fc_b)
-            # d(proj bias) = colsum(dx) rides on this pass (dx is its residual input)
-            self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx,
-                           Lg.proj_b)
+            self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx, Lg.o_b,
+                           dm2, self._drop("resid1", l))
             dx, dx2 = dx2, dx
+            dm, dm2 = dm2, dm
+            dy = dm if dm is not None else dx
             # ---- attention block ----
-            ops.gemm(dx, Lp.o_w, self.datt, b_mn=True)
-            ops.gemm(dx, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
-            ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv)
+            ops.gemm(dy, Lp.o_w, self.datt, b_mn=True)
+            ops.gemm(dy, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
+            ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv,
+                              drop=self._drop("attn", l))
             if cfg.family == "llama":
                 ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
             ops.gemm(self.dqkv, Lp.qkv_w, self.dh, b_mn=True)
             ops.gemm(self.dqkv, self.h1[l], Lg.qkv_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.qkv_b is not None:
                 ops.colsum(self.dqkv, Lg.qkv_b)
-            self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx, Lg.o_b)
+            nxt = l - 1
+            self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx,
+                           G.layers[nxt].proj_b if nxt >= 0 else None, dm2 if nxt >= 0 else None,
+                           self._drop("resid2", nxt) if nxt >= 0 else None)
             dx, dx2 = dx2, dx
-        ops.embed_bwd(dx, self.ids, G.wte, G.wpe)
+            dm, dm2 = dm2, dm
+        ops.embed_bwd(dx, self.ids, G.wte, G.wpe, drop=self._drop("embd"))
         return self.loss
 
 

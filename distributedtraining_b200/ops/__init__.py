@@ -20,6 +20,35 @@ EPI = {"none": 0, "bias": 1, "bias_gelu": 2, "bias_resid": 3, "dgelu": 4, "resid
 _counters = {"launches": 0}
 
 
+class DropoutRng:
+    """Device-resident dropout state {seed, step counter}: masks are regenerated from it in forward AND backward
+    (csrc/dropout.cuh); ``advance()`` is one tiny stream-ordered kernel, so a captured training step replays with fresh masks."""
+
+    def __init__(self, device, seed: int = 0):
+        self.state = torch.tensor([seed & 0x7FFFFFFF, 0, 0, 0], dtype=torch.int32, device=device)
+
+    def advance(self) -> None:
+        if use_kernels(self.state):
+            _c(_lib.lib().dtb_rng_advance(_lib.ptr(self.state), _lib.stream_ptr()), "rng_advance")
+            _tick()
+        else:
+            self.state[1] += 1
+
+
+class Drop:
+    """One dropout site: (rng state, site/stream id, probability)."""
+    __slots__ = ("rng", "stream", "p")
+
+    def __init__(self, rng: DropoutRng, stream: int, p: float):
+        self.rng, self.stream, self.p = rng, int(stream), float(p)
+
+
+def _drop_args(drop):
+    if drop is None or drop.p <= 0.0:
+        return None, 0, ctypes.c_float(0.0)
+    return _lib.ptr(drop.rng.state), drop.stream, ctypes.c_float(drop.p)
+
+
 def launch_count() -> int:
     """Number of hand-written kernel launches issued through this module (for bench.py's ``gpu_launches``)."""
     return _counters["launches"]
@@ -44,7 +73,7 @@ def _row_major(t: torch.Tensor, what: str) -> int:
 # GEMM
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=0, b2=None, b_persist=None):
+         splits=0, b2=None, b_persist=None, drop=None):
     """out[M,N] = epi(alpha * A @ B^T) -- see :func:`reference.gemm` for the operand conventions.
 
     CUDA: persistent tcgen05/TMEM/TMA kernel (csrc/sm100_gemm.cu).  fp32 ``out`` is always reduce-ADDED by TMA
@@ -54,10 +83,11 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     validator's ``theta_base + delta_i`` eval without materialising the sum; B2 may live in a peer window).
     ``b_persist``: local destination of the same shape as ``b`` -- when ``b`` is read from a PEER window (fused
     broadcast -> first forward GEMM) every B tile is also TMA-stored there while the MMA consumes it.
+    ``drop`` (``Drop``, residual epilogues only): ``out = aux + dropout(alpha A B^T + bias)``, mask generated in the epilogue.
     """
     if not use_kernels(out):
         return ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
-                        accumulate=accumulate, b2=b2, b_persist=b_persist)
+                        accumulate=accumulate, b2=b2, b_persist=b_persist, drop=drop)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb, ldc = _row_major(a, "a"), _row_major(b, "b"), _row_major(out, "out")
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -82,7 +112,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
         _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), int(out_f32), EPI[epi],
         _lib.ptr(bias), _lib.ptr(aux), ldaux, _lib.ptr(out2), ldc2, ctypes.c_float(alpha), splits, _lib.num_sms(),
         _lib.stream_ptr(), _lib.ptr(b2), _row_major(b2, "b2") if b2 is not None else 0, _lib.ptr(b_persist),
-        _row_major(b_persist, "b_persist") if b_persist is not None else 0)
+        _row_major(b_persist, "b_persist") if b_persist is not None else 0, *_drop_args(drop))
     _c(rc, "gemm")
     _tick()
     return out
@@ -116,19 +146,19 @@ def quantize_fp8(x, q, st: "Fp8Scale"):
     return q
 
 
-def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=None, aux=None, out2=None):
+def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=None, aux=None, out2=None, drop=None):
     """out[M,N] (bf16) = epi(sa*sb * A8 @ B8^T) with e4m3 operands (K-major), fp32 accumulation on kind::f8f6f4 tensor cores."""
     if not use_kernels(out):
         A = a8.view(torch.float8_e4m3fn).float() * sa.scale
         B = b8.view(torch.float8_e4m3fn).float() * sb.scale
-        return ref.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2)
+        return ref.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2, drop=drop)
     M, K = a8.shape
     N = b8.shape[0]
     assert b8.shape[1] == K and out.dtype == torch.bfloat16 and K % 16 == 0
     rc = _lib.lib().dtb_gemm_fp8(_lib.ptr(a8), _lib.ptr(b8), _lib.ptr(out), M, N, K, a8.stride(0), b8.stride(0), out.stride(0),
                                  EPI[epi], _lib.ptr(bias), _lib.ptr(aux), _row_major(aux, "aux") if aux is not None else 0,
                                  _lib.ptr(out2), _row_major(out2, "out2") if out2 is not None else 0, ctypes.c_float(1.0),
-                                 _lib.num_sms(), _lib.stream_ptr(), _lib.ptr(sa.scale), _lib.ptr(sb.scale))
+                                 _lib.num_sms(), _lib.stream_ptr(), _lib.ptr(sa.scale), _lib.ptr(sb.scale), *_drop_args(drop))
     _c(rc, "gemm_fp8")
     _tick()
     return out
@@ -137,28 +167,30 @@ def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=No
 # ---------------------------------------------------------------------------------------------------------------------
 # embedding / norms / activations / loss
 # ---------------------------------------------------------------------------------------------------------------------
-def embed_fwd(ids, wte, wpe, out, wte2=None, wpe2=None):
-    """out = wte[ids] + wpe[pos] (+ wte2[ids] + wpe2[pos]: a second table, e.g. a delta in a peer window)."""
+def embed_fwd(ids, wte, wpe, out, wte2=None, wpe2=None, drop=None):
+    """out = dropout(wte[ids] + wpe[pos] (+ wte2[ids] + wpe2[pos]: a second table, e.g. a delta in a peer window))."""
     if not use_kernels(out):
-        ref.embed_fwd(ids.long(), wte, wpe, out)
         if wte2 is not None:
+            assert drop is None
+            ref.embed_fwd(ids.long(), wte, wpe, out)
             tmp = torch.empty_like(out)
             ref.embed_fwd(ids.long(), wte2, wpe2, tmp)
             out.add_(tmp)
-        return out
+            return out
+        return ref.embed_fwd(ids.long(), wte, wpe, out, drop)
     M, d = out.shape
     _c(_lib.lib().dtb_embed_fwd(_lib.ptr(ids), _lib.ptr(wte), _lib.ptr(wpe), _lib.ptr(out), M, ids.shape[-1], d,
-                                _lib.stream_ptr(), _lib.ptr(wte2), _lib.ptr(wpe2)), "embed_fwd")
+                                _lib.stream_ptr(), _lib.ptr(wte2), _lib.ptr(wpe2), *_drop_args(drop)), "embed_fwd")
     _tick()
     return out
 
 
-def embed_bwd(dx, ids, dwte, dwpe):
+def embed_bwd(dx, ids, dwte, dwpe, drop=None):
     if not use_kernels(dx):
-        return ref.embed_bwd(dx, ids.long(), dwte, dwpe)
+        return ref.embed_bwd(dx, ids.long(), dwte, dwpe, drop)
     M, d = dx.shape
     _c(_lib.lib().dtb_embed_bwd(_lib.ptr(dx), _lib.ptr(ids), _lib.ptr(dwte), _lib.ptr(dwpe), M, ids.shape[-1], d,
-                                _lib.stream_ptr()), "embed_bwd")
+                                _lib.stream_ptr(), *_drop_args(drop)), "embed_bwd")
     _tick()
 
 
@@ -172,21 +204,30 @@ def layernorm_fwd(x, w, b, eps, out, mean, rstd):
     return out
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None, dcol=None):
-    """``dcol`` (fp32 [d], optional): += column sums of ``dresid`` -- the bias gradient of the GEMM that fed the residual
-    branch, folded into this pass instead of a separate colsum launch."""
+def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None, dcol=None, dxm=None, drop=None):
+    """dx_out = LN'(dy) (+ dresid).  Two optional riders on the same pass:
+
+    ``dxm`` + ``drop``: a second, dropout-masked copy of dx_out -- the dY of the GEMM whose output went through dropout
+    site ``drop`` on its way into this residual stream (mask regenerated from the counter, never stored);
+    ``dcol`` (fp32 [d]): += column sums of that dY (``dxm`` when given, else ``dx_out``) = the GEMM's bias gradient,
+    instead of a separate colsum launch."""
+    masked = dxm is not None and drop is not None and drop.p > 0
     if not use_kernels(dx_out):
+        ref.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
+        if masked:
+            ref.masked_copy(dx_out, dxm, drop)
         if dcol is not None:
-            ref.colsum(dresid, dcol)
-        return ref.layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid)
+            ref.colsum(dxm if masked else dx_out, dcol)
+        return dx_out
     M, d = x.shape
-    fold = dcol is not None and d == 768 and dresid is not None
-    if dcol is not None and not fold:
-        colsum(dresid, dcol)
+    fold = dcol is not None and d == 768
     _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dresid),
                                _lib.ptr(dx_out), _lib.ptr(dw), _lib.ptr(db), M, d, 0, _lib.num_sms(), _lib.stream_ptr(),
-                               _lib.ptr(dcol) if fold else None), "layernorm_bwd")
+                               _lib.ptr(dcol) if fold else None, _lib.ptr(dxm) if masked else None,
+                               *_drop_args(drop if masked else None)), "layernorm_bwd")
     _tick()
+    if dcol is not None and not fold:
+        colsum(dxm if masked else dx_out, dcol)
     return dx_out
 
 
@@ -205,8 +246,8 @@ def rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid=None):
         return ref.rmsnorm_bwd(dy, x, w, rstd, dx_out, dw, dresid)
     M, d = x.shape
     _c(_lib.lib().dtb_norm_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), None, _lib.ptr(rstd), _lib.ptr(dresid),
-                               _lib.ptr(dx_out), _lib.ptr(dw), None, M, d, 1, _lib.num_sms(), _lib.stream_ptr(), None),
-       "rmsnorm_bwd")
+                               _lib.ptr(dx_out), _lib.ptr(dw), None, M, d, 1, _lib.num_sms(), _lib.stream_ptr(), None, None,
+                               None, 0, ctypes.c_float(0.0)), "rmsnorm_bwd")
     _tick()
     return dx_out
 
@@ -262,14 +303,14 @@ def colsum(x, out):
 # ---------------------------------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
     from . import attention as _att
-    return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv)
+    return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop)
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
     from . import attention as _att
-    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)
+    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -19,28 +19,29 @@ def _kernel_ok(qkv, T, hd) -> bool:
     return hasattr(L, "dtb_attention_fwd") and hd == 64
 
 
-def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
     Hkv = Hkv or H
     if _kernel_ok(qkv, T, hd):
-        from . import _tick
+        from . import _drop_args, _tick
         rc = _lib.lib().dtb_attention_fwd(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(lse), B, T, H, Hkv, hd, qkv.stride(0),
-                                          out.stride(0), ctypes.c_float(1.0 / math.sqrt(hd)), _lib.stream_ptr())
+                                          out.stride(0), ctypes.c_float(1.0 / math.sqrt(hd)), _lib.stream_ptr(),
+                                          *_drop_args(drop))
         if rc != 0:
             raise RuntimeError(f"attention_fwd kernel failed ({rc})")
         _tick()
         return out
-    return ref.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv)
+    return ref.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop)
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
     Hkv = Hkv or H
     if _kernel_ok(qkv, T, hd) and hasattr(_lib.lib(), "dtb_attention_bwd"):
-        from . import _tick
+        from . import _drop_args, _tick
         rc = _lib.lib().dtb_attention_bwd(_lib.ptr(dout), _lib.ptr(qkv), _lib.ptr(out), _lib.ptr(lse), _lib.ptr(dqkv), B, T,
                                           H, Hkv, hd, qkv.stride(0), out.stride(0), ctypes.c_float(1.0 / math.sqrt(hd)),
-                                          _lib.stream_ptr())
+                                          _lib.stream_ptr(), *_drop_args(drop))
         if rc != 0:
             raise RuntimeError(f"attention_bwd kernel failed ({rc})")
         _tick()
         return dqkv
-    return ref.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)
+    return ref.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop)

@@ -15,6 +15,67 @@ GELU_K0 = math.sqrt(2.0 / math.pi)
 GELU_K1 = 0.044715
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# counter-based dropout masks: the same arithmetic as csrc/dropout.cuh (uint32 math carried in int64)
+# ---------------------------------------------------------------------------------------------------------------------
+M32 = 0xFFFFFFFF
+
+
+def _mix32s(x):
+    x = (x * 0x7FEB352D) & M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & M32
+    return x ^ (x >> 16)
+
+
+def _mix32(x):
+    return _mix32s(x ^ (x >> 16))
+
+
+def drop_thr(p: float) -> int:
+    return int(p * 65536.0 + 0.5)
+
+
+def drop_key(state, stream: int) -> int:
+    """``state``: int32[4] tensor {seed, counter, -, -} (or a (seed, counter) tuple) -> the per-site 32-bit key."""
+    seed, counter = (int(v) & M32 for v in (state[:2].tolist() if torch.is_tensor(state) else state[:2]))
+    k = _mix32((seed + counter * 0x9E3779B9) & M32)
+    return _mix32(k ^ ((stream * 0x85EBCA6B + 0xC2B2AE35) & M32))
+
+
+def _bits16(word, odd):
+    return torch.where(odd, word >> 16, word & 0xFFFF)
+
+
+def drop_mult_2d(state, stream: int, p: float, M: int, d: int, device) -> torch.Tensor:
+    """[M, d] fp32 multipliers (0 or 1/(1-p)) of a dropout site over a row-major [M, d] tensor."""
+    key = drop_key(state, stream)
+    r = torch.arange(M, dtype=torch.int64, device=device)[:, None]
+    c = torch.arange(d, dtype=torch.int64, device=device)[None, :]
+    pair = (r * (d >> 1) + (c >> 1)) & M32
+    bits = _bits16(_mix32s(pair ^ key), (c & 1).bool())
+    return (bits >= drop_thr(p)).float() * (1.0 / (1.0 - p))
+
+
+def drop_mult_attn(state, stream: int, p: float, B: int, T: int, H: int, device) -> torch.Tensor:
+    """[B, H, T, T] multipliers of the attention-probability dropout: element (b, h, i, j) is keyed by the q head, the
+    global q row b*T + i and the global key token b*T + j."""
+    key = drop_key(state, stream)
+    M = B * T
+    h = torch.arange(H, dtype=torch.int64, device=device)[None, :, None, None]
+    b = torch.arange(B, dtype=torch.int64, device=device)[:, None, None, None]
+    i = torch.arange(T, dtype=torch.int64, device=device)[None, None, :, None]
+    j = torch.arange(T, dtype=torch.int64, device=device)[None, None, None, :]
+    rowkey = _mix32((h * M + b * T + i) & M32 ^ key)
+    kg = b * T + j
+    bits = _bits16(_mix32s((kg >> 1) ^ rowkey), (kg & 1).bool())
+    return (bits >= drop_thr(p)).float() * (1.0 / (1.0 - p))
+
+
+def _drop_mult(drop, M, d, device):
+    return None if drop is None or drop.p <= 0 else drop_mult_2d(drop.rng.state, drop.stream, drop.p, M, d, device)
+
+
 def gelu_tanh(x: torch.Tensor) -> torch.Tensor:
     return F.gelu(x, approximate="tanh")
 
@@ -28,7 +89,7 @@ def dgelu_tanh(x: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=1, b2=None, b_persist=None):
+         splits=1, b2=None, b_persist=None, drop=None):
     """out[M,N] = epi(alpha * A @ B^T).  ``a`` is stored [M,K] (K-major) or [K,M] (``a_mn``); ``b`` [N,K] or [K,N]."""
     A = a.t() if a_mn else a
     if b_persist is not None:
@@ -43,6 +104,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
             out2.copy_(acc.to(out2.dtype))
         acc = gelu_tanh(acc)
     elif epi in ("bias_resid", "resid"):
+        mult = _drop_mult(drop, acc.shape[0], acc.shape[1], acc.device)
+        if mult is not None:  # out = resid + dropout(A B^T + bias)
+            acc = acc * mult
         acc = acc + aux.float()
     elif epi == "dgelu":
         acc = acc * dgelu_tanh(aux.float())
@@ -55,20 +119,26 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     return out
 
 
-def embed_fwd(ids, wte, wpe, out):
+def embed_fwd(ids, wte, wpe, out, drop=None):
     T = ids.shape[-1]
     x = wte[ids.reshape(-1)].float()
     if wpe is not None:
         pos = torch.arange(T, device=ids.device).repeat(ids.numel() // T)
         x = x + wpe[pos].float()
+    mult = _drop_mult(drop, x.shape[0], x.shape[1], x.device)
+    if mult is not None:
+        x = x * mult
     out.copy_(x.to(out.dtype))
     return out
 
 
-def embed_bwd(dx, ids, dwte, dwpe):
+def embed_bwd(dx, ids, dwte, dwpe, drop=None):
     """dwte[V,d] += scatter(dx); dwpe[T,d] += sum over batch.  fp32 accumulators."""
     T = ids.shape[-1]
     d = dx.shape[-1]
+    mult = _drop_mult(drop, dx.numel() // d, d, dx.device)
+    if mult is not None:
+        dx = dx.reshape(-1, d).float() * mult
     dwte.index_add_(0, ids.reshape(-1), dx.reshape(-1, d).to(dwte.dtype))
     if dwpe is not None:
         dwpe[:T].add_(dx.reshape(-1, T, d).to(dwpe.dtype).sum(0))
@@ -84,6 +154,13 @@ def layernorm_fwd(x, w, b, eps, out, mean, rstd):
     mean.copy_(mu)
     rstd.copy_(rs)
     return out
+
+
+def masked_copy(dx_out, dxm, drop):
+    """dxm = dropout-masked copy of dx_out (the dY of the GEMM whose output went through dropout site ``drop``)."""
+    mult = _drop_mult(drop, dx_out.shape[0], dx_out.shape[1], dx_out.device)
+    dxm.copy_((dx_out.float() * mult).to(dxm.dtype))
+    return dxm
 
 
 def layernorm_bwd(dy, x, w, mean, rstd, dx_out, dw, db, dresid=None):
@@ -128,8 +205,9 @@ def _split_qkv(qkv, B, T, H, Hkv, hd):
     return q, k, v
 
 
-def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
-    """Causal self-attention over packed qkv [B*T, (H+2Hkv)*hd] -> out [B*T, H*hd]; lse [B,H,T] fp32 (natural log)."""
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
+    """Causal self-attention over packed qkv [B*T, (H+2Hkv)*hd] -> out [B*T, H*hd]; lse [B,H,T] fp32 (natural log).
+    ``drop``: dropout on the softmax probabilities (the normaliser / lse are those of the un-dropped softmax)."""
     Hkv = Hkv or H
     q, k, v = _split_qkv(qkv, B, T, H, Hkv, hd)
     if Hkv != H:
@@ -140,6 +218,8 @@ def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
     s = s.masked_fill(~mask, float("-inf"))
     l = torch.logsumexp(s, dim=-1)
     p = torch.exp(s - l[..., None])
+    if drop is not None and drop.p > 0:
+        p = p * drop_mult_attn(drop.rng.state, drop.stream, drop.p, B, T, H, qkv.device)
     o = p @ v.float()
     out.copy_(o.transpose(1, 2).reshape(B * T, H * hd).to(out.dtype))
     if lse is not None:
@@ -147,7 +227,7 @@ def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None):
     return out
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
     Hkv = Hkv or H
     rep = H // Hkv
     q, k, v = _split_qkv(qkv, B, T, H, Hkv, hd)
@@ -160,8 +240,13 @@ def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None):
     s = (q @ kx.transpose(-1, -2)) * scale
     mask = torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
     p = torch.exp(s - lse[..., None]).masked_fill(~mask, 0.0)
-    dv = p.transpose(-1, -2) @ do
     dp = do @ vx.transpose(-1, -2)
+    if drop is not None and drop.p > 0:
+        mult = drop_mult_attn(drop.rng.state, drop.stream, drop.p, B, T, H, qkv.device)
+        dv = (p * mult).transpose(-1, -2) @ do
+        dp = dp * mult
+    else:
+        dv = p.transpose(-1, -2) @ do
     D = (do * o).sum(-1, keepdim=True)
     ds = p * (dp - D) * scale
     dq = ds @ kx

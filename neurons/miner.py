@@ -21,7 +21,8 @@ def main(argv=None):
     ctx = build_context("miner", argv)
     cfg = ctx.config
     batch_size = cfg.batch_size
-    trainer = Trainer(cfg.model, device=ctx.device, batch=batch_size, seq=cfg.seq_len, lr=cfg.lr, seed=0)
+    trainer = Trainer(cfg.model, device=ctx.device, batch=batch_size, seq=cfg.seq_len, lr=cfg.lr, seed=0,
+                      dropout=getattr(cfg, "dropout", None))
     maybe_resume(cfg, trainer, ctx.rank)
     # reference: WikiText-103 train split @ max_length 64, no shuffle (neurons/miner.py:54-106); offline: synthetic tokens
     data_loader = SyntheticTokens(batch_size, cfg.seq_len, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1,

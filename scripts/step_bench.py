@@ -12,11 +12,12 @@ ap.add_argument("--seq", type=int, default=64)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--no-graph", action="store_true")
-ap.add_argument("--lm-chunk", type=int, default=8192)
+ap.add_argument("--lm-chunk", type=int, default=16384)
 ap.add_argument("--fp8", action="store_true")
+ap.add_argument("--dropout", type=float, default=None)
 a = ap.parse_args()
 torch.manual_seed(0)
-tr = Trainer(a.model, device="cuda", batch=a.batch, seq=a.seq, lr=5e-4, use_graph=not a.no_graph, lm_chunk=a.lm_chunk, fp8_forward=a.fp8)
+tr = Trainer(a.model, device="cuda", batch=a.batch, seq=a.seq, lr=5e-4, use_graph=not a.no_graph, lm_chunk=a.lm_chunk, fp8_forward=a.fp8, dropout=a.dropout)
 V = tr.cfg.vocab_size
 pool = [torch.randint(0, V, (a.batch, a.seq), dtype=torch.int32, device="cuda") for _ in range(4)]
 losses = []

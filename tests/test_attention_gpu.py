@@ -34,3 +34,34 @@ def test_attention_fwd_bwd(B, T, H, Hkv):
         rel = (a - b).norm() / (b.norm() + 1e-8)
         assert rel < 3e-2, (name, float(rel))
         assert (a - b).abs().max().item() < 5e-2 * max(1.0, b.abs().max().item()), name
+
+
+@pytest.mark.parametrize("B,T,H,Hkv", [(4, 64, 2, 2), (3, 32, 2, 2), (2, 256, 2, 2), (1, 512, 4, 2), (3, 96, 2, 2)])
+def test_attention_dropout_fwd_bwd(B, T, H, Hkv):
+    """Dropout on the softmax probabilities: all five kernels regenerate the reference's (head, q row, key token) mask."""
+    torch.manual_seed(1)
+    hd = 64
+    M = B * T
+    rng = ops.DropoutRng("cuda", seed=77)
+    rng.advance()
+    drop = ops.Drop(rng, 4, 0.1)
+    qkv = (torch.randn(M, (H + 2 * Hkv) * hd, device="cuda") * 0.7).bfloat16()
+    out = torch.zeros(M, H * hd, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device="cuda")
+    ops.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop=drop)
+    r_out, r_lse = torch.empty(M, H * hd, device="cuda"), torch.empty(B, H, T, device="cuda")
+    ref.attention_fwd(qkv, r_out, r_lse, B, T, H, hd, Hkv, drop)
+    plain = torch.empty(M, H * hd, device="cuda")
+    ref.attention_fwd(qkv, plain, None, B, T, H, hd, Hkv)
+    assert (plain - r_out).abs().max().item() > 0.05  # the mask really changes the output
+    assert (out.float() - r_out).abs().max().item() < 2e-2 * max(1.0, r_out.abs().max().item())
+    assert (lse - r_lse).abs().max().item() < 2e-2
+    dout = (torch.randn(M, H * hd, device="cuda") * 0.5).bfloat16()
+    dqkv = torch.zeros_like(qkv)
+    ops.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop=drop)
+    r_dqkv = torch.empty(M, (H + 2 * Hkv) * hd, device="cuda")
+    ref.attention_bwd(dout, qkv, r_out.bfloat16(), r_lse, r_dqkv, B, T, H, hd, Hkv, drop)
+    parts = [H * hd, Hkv * hd, Hkv * hd]
+    for name, a, b in zip(["dq", "dk", "dv"], dqkv.float().split(parts, dim=1), r_dqkv.split(parts, dim=1)):
+        rel = (a - b).norm() / (b.norm() + 1e-8)
+        assert rel < 3e-2, (name, float(rel))

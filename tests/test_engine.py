@@ -158,3 +158,85 @@ def test_fp8_forward_trains_close_to_bf16():
         res[fp8] = [float(tr.step(ids[i % 4])) for i in range(12)]
     assert res[True][-1] < res[True][0]
     assert max(abs(a - b) for a, b in zip(res[False], res[True])) < 0.15, (res[False], res[True])
+
+
+def _with_dropout(name, p=0.1):
+    import dataclasses
+    return dataclasses.replace(get_config(name), dropout=p)
+
+
+def test_dropout_masks_are_counter_based_and_unbiased():
+    from distributedtraining_b200.ops import reference as ref
+    m0 = ref.drop_mult_2d((7, 1), 3, 0.1, 257, 128, "cpu")
+    assert torch.equal(m0, ref.drop_mult_2d((7, 1), 3, 0.1, 257, 128, "cpu"))          # pure function of the state
+    assert not torch.equal(m0, ref.drop_mult_2d((7, 2), 3, 0.1, 257, 128, "cpu"))      # counter changes the mask
+    assert not torch.equal(m0, ref.drop_mult_2d((7, 1), 4, 0.1, 257, 128, "cpu"))      # so does the site id
+    keep = (m0 > 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01 and abs(m0.mean().item() - 1.0) < 0.02
+    ma = ref.drop_mult_attn((7, 1), 1, 0.1, 3, 32, 4, "cpu")
+    assert ma.shape == (3, 4, 32, 32) and abs((ma > 0).float().mean().item() - 0.9) < 0.02
+
+
+def test_engine_dropout_matches_autograd_cpu():
+    """Train-mode dropout (embd / attn / resid, GPT-2's 0.1): the explicit engine and plain autograd agree when the
+    oracle applies the same counter-based masks; eval mode ignores dropout; consecutive steps use different masks."""
+    torch.manual_seed(0)
+    cfg = _with_dropout("gpt2-tiny")
+    cfg, man, arena = new_model(cfg)
+    arena.flat.add_(torch.randn_like(arena.flat) * 0.02)
+    B, T = 3, 16
+    ids = torch.randint(0, cfg.vocab_size, (B, T))
+    grads = torch.zeros_like(arena.flat)
+    eng = TransformerEngine(cfg, man, arena.flat, grads, B, T, lm_chunk=32)
+    eng.set_batch(ids.int())
+    l_eng = float(eng.forward_backward())
+    theta = arena.flat.clone().requires_grad_(True)
+    loss = oracle_loss(cfg, man, theta, ids, drop_state=eng.rng.state)
+    loss.backward()
+    assert abs(float(loss) - l_eng) < 1e-5
+    assert (theta.grad - grads).abs().max().item() < 1e-5
+    l_eval = float(eng.forward_loss())
+    assert abs(l_eval - float(oracle_loss(cfg, man, arena.flat, ids))) < 1e-5 and abs(l_eval - l_eng) > 1e-4
+    l_eng2 = float(eng.forward_backward())
+    assert abs(l_eng2 - l_eng) > 1e-6  # the counter advanced -> new masks
+
+
+@pytest.mark.gpu
+def test_engine_dropout_matches_autograd_gpu():
+    torch.manual_seed(0)
+    cfg, man, arena = new_model(_with_dropout("gpt2-tiny"))
+    arena.flat.add_(torch.randn_like(arena.flat) * 0.02)
+    B, T = 4, 64
+    flat = arena.flat.cuda()
+    p16 = flat.bfloat16()
+    ids = torch.randint(0, cfg.vocab_size, (B, T), device="cuda")
+    grads = torch.zeros_like(flat)
+    eng = TransformerEngine(cfg, man, p16, grads, B, T, lm_chunk=128)
+    eng.set_batch(ids.int())
+    l2 = eng.forward_backward()
+    theta = p16.float().requires_grad_(True)
+    loss = oracle_loss(cfg, man, theta, ids, drop_state=eng.rng.state)
+    loss.backward()
+    l_nodrop = oracle_loss(cfg, man, p16.float(), ids)
+    assert abs(float(loss) - float(l2)) < 3e-2 and abs(float(l_nodrop) - float(loss)) > 1e-3
+    bad = []
+    for s in man:
+        a, b = man.view(theta.grad, s.name), man.view(grads, s.name)
+        rel = (a - b).norm() / (a.norm() + 1e-8)
+        if rel > 6e-2:
+            bad.append((s.name, float(rel)))
+    assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_trainer_dropout_graph_replays_fresh_masks_gpu():
+    """The captured step regenerates its masks from the device counter: the same batch gives a different train loss on
+    every replay, and the eval loss (no dropout) is deterministic."""
+    torch.manual_seed(0)
+    tr = Trainer(_with_dropout("gpt2-tiny"), device="cuda", batch=8, seq=64, lr=0.0, seed=1, use_graph=True)
+    ids = torch.randint(0, 512, (8, 64), dtype=torch.int32, device="cuda")
+    losses = [float(tr.step(ids)) for _ in range(4)]   # lr = 0: identical weights, only the masks differ
+    assert len({round(l, 6) for l in losses}) == 4, losses
+    assert int(tr.engine.rng.state[1]) >= 4
+    e1, e2 = float(tr.eval_loss(ids)), float(tr.eval_loss(ids))
+    assert e1 == e2

@@ -320,3 +320,59 @@ def test_checksum_matches_cpu_and_detects_change():
     y = x.clone()
     y[1234] += 1e-3
     assert ops.checksum(y) != c_gpu
+
+
+def test_dropout_sites_match_reference_masks():
+    """Every kernel that applies (or re-applies) a dropout site regenerates exactly the reference's counter-based mask."""
+    torch.manual_seed(11)
+    rng = ops.DropoutRng(DEV, seed=123)
+    rng.advance(); rng.advance()
+    assert rng.state.tolist()[:2] == [123, 2]
+    # GEMM residual epilogue: out = aux + dropout(A B^T + bias)
+    M, N, K = 384, 768, 256
+    a, b, bias, aux = _bf(M, K), _bf(N, K, scale=0.1), _bf(N), _bf(M, N)
+    out, r = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV)
+    dr = ops.Drop(rng, 5, 0.1)
+    ops.gemm(a, b, out, epi="bias_resid", bias=bias, aux=aux, drop=dr)
+    ref.gemm(a, b, r, epi="bias_resid", bias=bias, aux=aux, drop=dr)
+    _close(out, r)
+    dropped = (ref.drop_mult_2d(rng.state, 5, 0.1, M, N, DEV) == 0)
+    assert torch.equal(out[dropped], aux[dropped]) and 0.08 < dropped.float().mean().item() < 0.12
+    # embedding fwd / bwd
+    V, T, d = 1000, 64, 768
+    ids = torch.randint(0, V, (4, T), device=DEV, dtype=torch.int32)
+    wte, wpe = _bf(V, d), _bf(T, d)
+    x, rx = torch.empty(4 * T, d, device=DEV, dtype=torch.bfloat16), torch.empty(4 * T, d, device=DEV)
+    ops.embed_fwd(ids, wte, wpe, x, drop=ops.Drop(rng, 0, 0.1))
+    ref.embed_fwd(ids.long(), wte, wpe, rx, ops.Drop(rng, 0, 0.1))
+    _close(x, rx)
+    dx = _bf(4 * T, d)
+    g1, g2 = torch.zeros(V, d, device=DEV), torch.zeros(T, d, device=DEV)
+    r1, r2 = torch.zeros(V, d, device=DEV), torch.zeros(T, d, device=DEV)
+    ops.embed_bwd(dx, ids, g1, g2, drop=ops.Drop(rng, 0, 0.1))
+    ref.embed_bwd(dx, ids.long(), r1, r2, ops.Drop(rng, 0, 0.1))
+    _close(g1, r1, rtol=1e-4); _close(g2, r2, rtol=1e-4)
+
+
+@pytest.mark.parametrize("d", [768, 1024, 128])
+def test_layernorm_bwd_masked_copy_and_bias_fold(d):
+    torch.manual_seed(12)
+    M = 515
+    rng = ops.DropoutRng(DEV, seed=9)
+    rng.advance()
+    x, w = _bf(M, d) + 0.3, _bf(d) + 1.0
+    mean, rstd = x.float().mean(-1), torch.rsqrt(x.float().var(-1, unbiased=False) + 1e-5)
+    dy, dres = _bf(M, d), _bf(M, d)
+    for drop in (None, ops.Drop(rng, 7, 0.1)):
+        dx, dxm = torch.empty(M, d, device=DEV, dtype=torch.bfloat16), torch.zeros(M, d, device=DEV, dtype=torch.bfloat16)
+        dw, db, dcol = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+        ops.layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, dres, dcol, dxm if drop else None, drop)
+        rdx, rdw, rdb = torch.empty(M, d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+        ref.layernorm_bwd(dy, x, w, mean, rstd, rdx, rdw, rdb, dres)
+        _close(dx, rdx, rtol=1e-2); _close(dw, rdw, rtol=1e-3); _close(db, rdb, rtol=1e-3)
+        if drop is None:
+            _close(dcol, dx.float().sum(0), rtol=2e-3)
+        else:
+            want = dx.float() * ref.drop_mult_2d(rng.state, 7, 0.1, M, d, DEV)
+            _close(dxm, want, rtol=1e-2)
+            _close(dcol, want.sum(0), rtol=5e-3)
