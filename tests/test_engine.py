@@ -217,8 +217,8 @@ def test_engine_dropout_matches_autograd_gpu():
     theta = p16.float().requires_grad_(True)
     loss = oracle_loss(cfg, man, theta, ids, drop_state=eng.rng.state)
     loss.backward()
-    l_nodrop = oracle_loss(cfg, man, p16.float(), ids)
-    assert abs(float(loss) - float(l2)) < 3e-2 and abs(float(l_nodrop) - float(loss)) > 1e-3
+    assert abs(float(loss) - float(l2)) < 3e-2
+    assert 0.05 < (eng.xs[0] == 0).float().mean().item() < 0.15  # the embedding-dropout site really dropped ~10 %
     bad = []
     for s in man:
         a, b = man.view(theta.grad, s.name), man.view(grads, s.name)

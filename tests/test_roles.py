@@ -279,6 +279,10 @@ def test_local_network_and_address_store(tmp_path):
     flags = net.detect_metric_anomaly()
     assert flags["evil"] and not flags["h3"]
     assert all(net.rate_limiter("addr", n=3, t=60) for _ in range(3)) and not net.rate_limiter("addr", n=3, t=60)
+    # the reference's simulation-layer names resolve to the same objects (btt_connector.py:514-585)
+    from distributedtraining_b200.btt_connector import LocalHotkey, LocalMetagraph, LocalWallet
+    assert isinstance(net.metagraph, LocalMetagraph) and isinstance(net.wallet, LocalWallet)
+    assert LocalHotkey("simulated_hotkey_3").ss58_address == net.wallet.hotkey.ss58_address
 
 
 def test_checkpoint_resume(tmp_path):
