@@ -31,18 +31,20 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;   // one 128B swizzle atom of bf16
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;       // 1-SM: 48 KB x 4 stages
-constexpr int kStages2 = 6;                          // 2-SM: (16 KB A + 16 KB half-B) x 6 stages
+constexpr int kStageBytes = kABytes + kBBytes;       // 1-SM: 48 KB x 3 stages
+constexpr int kStages2 = 5;                          // 2-SM: (16 KB A + 16 KB half-B) x 5 stages
 constexpr int kStageBytes2 = kABytes + kBBytes / 2;
+constexpr int kRingBytes = kStages2 * kStageBytes2 > kStages * kStageBytes ? kStages2 * kStageBytes2 : kStages * kStageBytes;
 constexpr int kSlabBytes = BLOCK_M * 128;       // 16 KB: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
-constexpr int kNumSlabBufs = 2;
+constexpr int kNumSlabBufs = 4;                 // two per epilogue group: staging is double-buffered
 constexpr int kTmemCols = 512;
 constexpr int kNumThreads = 352;                // warp0 TMA, warp1 MMA, warps2-9 epilogue (2 groups of 4), warp10 persist
 constexpr int kEpiThreads = 256;
-constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNumSlabBufs * kSlabBytes + BLOCK_N * 4 /*bias*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kRingBytes + kNumSlabBufs * kSlabBytes + BLOCK_N * 4 /*bias*/ + 256 /*barriers*/;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Epi : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_RESID = 3, EPI_DGELU = 4, EPI_RESID = 5 };
 
@@ -120,16 +122,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kNStages = CL == 2 ? kStages2 : kStages;
   constexpr int kStgBytes = CL == 2 ? kStageBytes2 : kStageBytes;
-  static_assert(kStages2 * kStageBytes2 == kStages * kStageBytes, "same ring footprint");
   uint8_t* smem_ab = smem;
-  uint8_t* smem_slab = smem + kNStages * kStgBytes;
+  uint8_t* smem_slab = smem + kRingBytes;
   float* smem_bias = reinterpret_cast<float*>(smem_slab + kNumSlabBufs * kSlabBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BLOCK_N);
   uint64_t* empty_bar = full_bar + kNStages;
   uint64_t* tmem_full_bar = empty_bar + kNStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* aux_bars = tmem_empty_bar + 2;  // [2] one per epilogue group
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bars + 2);
+  uint64_t* aux_bars = tmem_empty_bar + 2;  // [4] one per epilogue group and staging buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bars + 4);
 
   const uint32_t warp_idx = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -146,7 +147,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], CL * (kEpiThreads / 32));  // 2-SM: the epilogue warps of BOTH CTAs arrive on the leader
-      mbar_init(&aux_bars[i], 1);
+      mbar_init(&aux_bars[2 * i], 1);
+      mbar_init(&aux_bars[2 * i + 1], 1);
     }
     fence_barrier_init();
   }
@@ -316,9 +318,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     }
   } else {
     // ===================== epilogue (warps 2..9): two independent groups of 4 warps =====================
-    // Group g handles slabs g, g+2, ... of every tile with its own staging buffer, named barrier, aux mbarrier and TMA
-    // issuer thread.  Two warps per SM sub-partition hide the ALU/MUFU latency of the fused epilogues; the aux tile
-    // (residual / pre-activation) is TMA-loaded INTO the staging buffer and transformed in place.
+    // Group g handles slabs g, g+2, ... of every tile with its own PAIR of staging buffers, named barrier, aux mbarriers
+    // and TMA issuer thread.  Two warps per SM sub-partition hide the ALU/MUFU latency of the fused epilogues.  Work items
+    // (tile, slab) alternate between the two buffers, so the TMA store of item i drains while item i+1 is computed, and the
+    // aux tile (residual / pre-activation) of item i+1 is TMA-loaded into the other buffer while item i is processed (the
+    // first slab of the NEXT tile is prefetched across the tile boundary) and transformed in place.  The measured cost of
+    // the single-buffered version was one exposed store-drain + one exposed aux load latency per slab (short-K GEMMs with
+    // a residual epilogue ran at 0.6 PF).
     const uint32_t ewarp = warp_idx - 2;             // 0..7
     const uint32_t grp = ewarp >> 2;                 // 0 / 1
     const uint32_t quad = warp_idx & 3;              // TMEM lane quadrant this warp may access
@@ -326,23 +332,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     const uint32_t epi_tid = threadIdx.x - 64;       // 0..255
     const bool issuer = (lane == 0) && ((ewarp & 3) == 0);  // one issuer thread per group
     const uint32_t bar_id = 1 + grp;                 // named barriers 1 / 2 (group-local, 128 threads)
-    uint8_t* buf = smem_slab + grp * kSlabBytes;
-    uint64_t* aux_bar = tmem_empty_bar + 2 + grp;    // after tmem_empty[2]
-    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
+    uint8_t* const buf0 = smem_slab + (2 * grp) * kSlabBytes;
+    uint8_t* const buf1 = buf0 + kSlabBytes;
+    uint64_t* const aux_bar = aux_bars + 2 * grp;    // [2], one per buffer
+    uint32_t acc = 0, acc_phase = 0, aux_phase = 0 /* bit b = parity of aux_bar[b] */, item = 0;
     const float alpha_eff = p.alpha * (p.scale_a ? (*p.scale_a) * (*p.scale_b) : 1.f);
     constexpr int kColsPerSlab = OUT_F32 ? 32 : 64;
     constexpr int kSlabs = BLOCK_N / kColsPerSlab;
     const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
-    const bool has_aux = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
+    const bool has_aux = !OUT_F32 && (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
     const bool dual = (p.epi == EPI_BIAS_GELU);
     const uint32_t dthr = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID) ? p.drop.thr : 0u;
     const uint32_t dkey = dthr ? drop_key(p.drop.rng, p.drop.stream) : 0u;
+    auto issue_aux = [&](int w, int sl, uint32_t b) {  // issuer only: aux slab of work item (w, sl) -> staging buffer b
+      const int n_t = w % p.tiles_n;
+      const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
+      mbar_expect_tx(&aux_bar[b], kSlabBytes);
+      tma_load_2d(b ? buf1 : buf0, &p.tmap_aux, &aux_bar[b], n_t * BLOCK_N + sl * kColsPerSlab, m_t * BLOCK_M);
+    };
+    if (has_aux && issuer && cluster_id < total_work) issue_aux(cluster_id, int(grp), 0);
     for (int w = cluster_id; w < total_work; w += num_clusters) {
       const int n_t = w % p.tiles_n;
       const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
       const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
       const int row = m0 + int(row_l);
-      const bool row_ok = row < p.M;
       if (has_bias) {
         named_bar_sync(3, kEpiThreads);  // previous tile's readers of smem_bias are done
         for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) {
@@ -355,10 +368,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + acc * BLOCK_N + ((quad * 32u) << 16);
 #pragma unroll 1
-      for (int s = grp; s < kSlabs; s += 2) {
+      for (int s = grp; s < kSlabs; s += 2, ++item) {
         const int c0 = s * kColsPerSlab;  // column offset inside the tile
         const int gcol0 = n0 + c0;
         const bool last = (s + 2 >= kSlabs);
+        const uint32_t b = dual ? 0u : (item & 1u);
+        uint8_t* const buf = b ? buf1 : buf0;
         uint8_t* rowp = buf + row_l * 128;
         if constexpr (OUT_F32) {
           uint32_t r[32];
@@ -369,7 +384,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             __syncwarp();
             if (lane == 0) { if constexpr (CL == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
           }
-          if (issuer) tma_store_wait_read<0>();
+          if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two items ago has drained
           named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
@@ -387,13 +402,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             tma_store_commit();
           }
         } else {
-          if (has_aux) {  // aux slab -> staging buffer (async), overlapped with the TMEM read below
-            if (issuer) {
-              tma_store_wait_read<0>();
-              mbar_expect_tx(aux_bar, kSlabBytes);
-              tma_load_2d(buf, &p.tmap_aux, aux_bar, gcol0, m0);
-            }
-          }
           uint32_t r[64];
           tmem_ld_32x32b_x32(taddr_row + c0, r);
           tmem_ld_32x32b_x32(taddr_row + c0 + 32, r + 32);
@@ -404,12 +412,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             if (lane == 0) { if constexpr (CL == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
           }
           if (has_aux) {
-            mbar_wait(aux_bar, aux_phase);
-            aux_phase ^= 1;
+            if (issuer) {  // prefetch the aux slab of the NEXT work item into the other buffer
+              int nw = w, ns = s + 2;
+              if (ns >= kSlabs) { nw = w + num_clusters; ns = int(grp); }
+              if (nw < total_work) {
+                tma_store_wait_read<0>();  // the previous item's store (issued one TMEM read ago) has left that buffer
+                issue_aux(nw, ns, b ^ 1u);
+              }
+            }
+            mbar_wait(&aux_bar[b], (aux_phase >> b) & 1u);
+            aux_phase ^= (1u << b);
           } else {
-            if (issuer) tma_store_wait_read<0>();
+            if (issuer) { if (dual) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             named_bar_sync(bar_id, 128);
           }
+          uint8_t* rowp2 = buf1 + row_l * 128;  // dual: gelu(u) tile
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float v[8];
@@ -455,35 +472,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
             *reinterpret_cast<uint4*>(rowp + sw) = o;
-            if (dual) {  // keep gelu(u) in registers (re-packed into r) for the second store
-              // (direct 16 B global stores of u were tried instead of the second TMA round trip: 813 vs 868 TFLOP/s -- kept TMA)
+            if (dual) {  // second output gelu(u) goes to the group's other buffer in the same pass
 #pragma unroll
               for (int i = 0; i < 8; i += 2) gelu_tanh_pair(v[i], v[i + 1]);
-              r[ch * 4 + 0] = pack_bf16x2(v[0], v[1]); r[ch * 4 + 1] = pack_bf16x2(v[2], v[3]);
-              r[ch * 4 + 2] = pack_bf16x2(v[4], v[5]); r[ch * 4 + 3] = pack_bf16x2(v[6], v[7]);
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(rowp2 + sw) = o;
             }
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
           if (issuer) {
-            if (gcol0 < p.N) tma_store_2d(dual ? &p.tmap_c2 : &p.tmap_c, buf, gcol0, m0);
+            if (gcol0 < p.N) {
+              tma_store_2d(dual ? &p.tmap_c2 : &p.tmap_c, buf, gcol0, m0);
+              if (dual) tma_store_2d(&p.tmap_c, buf1, gcol0, m0);
+            }
             tma_store_commit();
-          }
-          if (dual) {  // second output: gelu(pre-activation) through the same buffer
-            if (issuer) tma_store_wait_read<0>();
-            named_bar_sync(bar_id, 128);
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              uint4 o;
-              o.x = r[ch * 4 + 0]; o.y = r[ch * 4 + 1]; o.z = r[ch * 4 + 2]; o.w = r[ch * 4 + 3];
-              *reinterpret_cast<uint4*>(rowp + ((ch ^ (row_l & 7)) << 4)) = o;
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(bar_id, 128);
-            if (issuer) {
-              if (gcol0 < p.N) tma_store_2d(&p.tmap_c, buf, gcol0, m0);
-              tma_store_commit();
-            }
           }
         }
       }

@@ -22,6 +22,9 @@ class KernelLibraryMissing(RuntimeError):
 
 @lru_cache(maxsize=1)
 def lib() -> ctypes.CDLL:
+    alt = os.environ.get("DTB200_LIB")  # A/B harness: load another build of the same C ABI
+    if alt:
+        return ctypes.CDLL(alt, mode=ctypes.RTLD_GLOBAL)
     if not LIB_PATH.exists():
         raise KernelLibraryMissing(
             f"{LIB_PATH} not found: run `python -m distributedtraining_b200.ops.build` (or __graft_entry__.build()) first")
