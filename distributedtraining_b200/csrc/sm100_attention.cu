@@ -37,6 +37,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct AttnParams {
   CUtensorMap tmap_qkv;  // [M, qkv_dim], box 64 x 128
   CUtensorMap tmap_do;   // [M, H*64],   box 64 x 128 (backward)
+  CUtensorMap tmap_out;  // forward: out [M, H*64]; backward: dqkv [M, qkv_dim]; box 64 x 128 (single-block kernels store by TMA)
   const __nv_bfloat16* o;
   const __nv_bfloat16* dout;
   __nv_bfloat16* out;    // forward output / backward dqkv
@@ -265,9 +266,17 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 template <bool WRITE_P>
 DTB_DEVICE void bwd_softmax_tiles(uint32_t tS, uint32_t tDP, uint32_t lane_off, int tid, int c_lo, int c_hi, float sl2,
                                   float lse_l2, float Drow, float scale, uint8_t* sP, uint8_t* sDS, uint32_t rowkey, int k0,
-                                  uint32_t dthr, float dscale) {
+                                  uint32_t dthr, float dscale, int ch_lo = 0, int ch_hi = 3) {
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
+    if (ch < ch_lo || ch > ch_hi) {  // warp-uniformly masked chunk (see attn_fwd_small_kernel): P = dS = 0
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (WRITE_P) st_swz(sP + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
+        st_swz(sDS + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
+      }
+      continue;
+    }
     float s[32], dp[32];
     tmem_ld32(tS + lane_off + ch * 32, s);
     tmem_ld32(tDP + lane_off + ch * 32, dp);
@@ -670,14 +679,20 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
     }
   }
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_tok - q0;
+  // 32-column chunks this WARP has to look at: with T % 32 == 0 all 32 rows of a warp sit in one sequence, so the chunks left
+  // of the sequence start and right of the warp's last row are masked for every lane (T = 64: 1.5 of 4 chunks on average).
+  int ch_lo = 0, ch_hi = 3;
+  if (p.T % 32 == 0) {
+    ch_lo = c_lo >> 5;  // c_lo is warp-uniform and a multiple of 32
+    ch_hi = warp;       // columns beyond the warp's last row (warp * 32 + 31) are causal-masked
+  }
   const float sl2 = p.scale * kLog2e;
   const uint32_t rowkey = attn_row_key(p, h, row_tok);
   mbar_wait(&bars[1], 0);
   tc_fence_after();
   float mx = -CUDART_INF_F;
 #pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    // chunk-level mask test is warp-uniform only when T % 32 == 0; the load is collective, so always load
+  for (int ch = ch_lo; ch <= ch_hi; ++ch) {
     float sv[32];
     tmem_ld32(tmem + lane_off + ch * 32, sv);
 #pragma unroll
@@ -690,6 +705,11 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   float lsum = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
+    if (ch < ch_lo || ch > ch_hi) {  // fully masked for this warp: P = 0
+#pragma unroll
+      for (int v = 0; v < 4; ++v) st_swz(sP + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
+      continue;
+    }
     float sv[32];
     tmem_ld32(tmem + lane_off + ch * 32, sv);
 #pragma unroll
@@ -728,21 +748,21 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-  __nv_bfloat16* dst = p.out + size_t(row_tok) * p.ld_out + h * kHd;
+  // O tile -> swizzled staging tile in the (dead) Q region -> ONE TMA store (rows >= M are clipped by the tensor map).
+  // Per-thread 16 B global stores of 32 different rows per instruction throttled the LSU (lg_throttle, ncu).
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
     float o[32];
     tmem_ld32(tmem + lane_off + ch * 32, o);
-    if (row_tok < p.M) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        uint4 q;
-        q.x = pack2(o[v * 8 + 0] * inv, o[v * 8 + 1] * inv); q.y = pack2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv);
-        q.z = pack2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv); q.w = pack2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv);
-        reinterpret_cast<uint4*>(dst)[ch * 4 + v] = q;
-      }
+    for (int v = 0; v < 4; ++v) {
+      uint4 q;
+      q.x = pack2(o[v * 8 + 0] * inv, o[v * 8 + 1] * inv); q.y = pack2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv);
+      q.z = pack2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv); q.w = pack2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv);
+      st_swz(sQ, tid, ch * 4 + v, q);
     }
   }
+  fence_proxy_async_smem();
   if (row_tok < p.M && p.lse) {
     const int b = row_tok / p.T, t = row_tok % p.T;
     p.lse[(size_t(b) * p.H + h) * p.T + t] = (m_ref + log2f(lsum)) * 0.6931471805599453f;
@@ -750,6 +770,12 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    if (elect_one()) {
+      tma_store_2d(&p.tmap_out, sQ, h * kHd, q0);
+      tma_store_commit();
+      tma_store_wait_read<0>();  // the staging tile must outlive the bulk read
+    }
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 128);
   }
@@ -826,8 +852,9 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = (row_tok < p.M) ? row_tok - q0 : -1;
   mbar_wait(&bars[1], 0);
   tc_fence_after();
+  const bool uni = (p.T % 32 == 0);  // chunk window of this warp, as in the forward kernel
   bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, p.scale * kLog2e, lse_l2, Drow, p.scale, sP, sDS,
-                          attn_row_key(p, h, row_tok), q0, p.drop.thr, p.drop.scale);
+                          attn_row_key(p, h, row_tok), q0, p.drop.thr, p.drop.scale, uni ? (c_lo >> 5) : 0, uni ? warp : 3);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -854,29 +881,37 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();
-  // thread = token row for all three outputs (q row for dQ, key row for dK/dV)
+  // thread = token row for all three outputs (q row for dQ, key row for dK/dV).  Every MMA has completed, so the operand
+  // tiles are dead: dQ / dK / dV are staged (swizzled) in the Q / K / dO tiles and leave as three TMA stores.
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {
     const uint32_t t = which == 0 ? tDQ : (which == 1 ? tDK : tDV);
-    __nv_bfloat16* dst = p.out + size_t(row_tok) * p.ld_out + (which == 0 ? colQ : (which == 1 ? colK : colV));
+    uint8_t* stage = smem + which * kTile;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       float o[32];
       tmem_ld32(t + lane_off + ch * 32, o);
-      if (row_tok < p.M) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint4 q;
-          q.x = pack2(o[v * 8 + 0], o[v * 8 + 1]); q.y = pack2(o[v * 8 + 2], o[v * 8 + 3]);
-          q.z = pack2(o[v * 8 + 4], o[v * 8 + 5]); q.w = pack2(o[v * 8 + 6], o[v * 8 + 7]);
-          reinterpret_cast<uint4*>(dst)[ch * 4 + v] = q;
-        }
+      for (int v = 0; v < 4; ++v) {
+        uint4 q;
+        q.x = pack2(o[v * 8 + 0], o[v * 8 + 1]); q.y = pack2(o[v * 8 + 2], o[v * 8 + 3]);
+        q.z = pack2(o[v * 8 + 4], o[v * 8 + 5]); q.w = pack2(o[v * 8 + 6], o[v * 8 + 7]);
+        st_swz(stage, tid, ch * 4 + v, q);
       }
     }
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    if (elect_one()) {
+      tma_store_2d(&p.tmap_out, smem, colQ, q0);
+      tma_store_2d(&p.tmap_out, smem + kTile, colK, q0);
+      tma_store_2d(&p.tmap_out, smem + 2 * kTile, colV, q0);
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -901,6 +936,7 @@ extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   p.tmap_do = p.tmap_qkv;
+  if (make_tmap_2d(&p.tmap_out, out, 2, uint64_t(H) * kHd, M, ld_out, 64, kBlk)) return 11;
   p.out = (__nv_bfloat16*)out; p.lse = lse; p.M = M; p.T = T; p.H = H; p.Hkv = Hkv; p.ld_out = ld_out; p.ld_o = ld_out;
   p.scale = scale;
   static bool cfg = false;
@@ -925,6 +961,7 @@ extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* 
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   if (make_tmap_2d(&p.tmap_do, dout, 2, uint64_t(H) * kHd, M, ld_o, 64, kBlk)) return 11;
+  if (make_tmap_2d(&p.tmap_out, dqkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   p.o = (const __nv_bfloat16*)o; p.dout = (const __nv_bfloat16*)dout; p.out = (__nv_bfloat16*)dqkv;
   p.lse = const_cast<float*>(lse); p.M = M; p.T = T; p.H = H; p.Hkv = Hkv; p.ld_out = ld_qkv; p.ld_o = ld_o; p.scale = scale;
   static bool cfg = false;
