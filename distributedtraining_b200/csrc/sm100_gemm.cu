@@ -71,6 +71,7 @@ struct GemmParams {
   int ldc2;
   float alpha;
   DropArgs drop;  // EPI_BIAS_RESID / EPI_RESID: out = aux + dropout(acc [+ bias])  (GPT-2 resid_pdrop)
+  float* colsum;  // optional fp32 [N]: += column sums of the bf16 output (e.g. the bias gradient that equals colsum(dY))
 };
 
 // GELU (tanh form, HF "gelu_new") with MUFU.TANH in fp32.  (A packed tanh.approx.bf16x2 variant halves the MUFU count but
@@ -489,6 +490,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             }
             tma_store_commit();
           }
+          if (p.colsum) {
+            // column sums of the staged [128 x 64] output slab (the bf16 values being stored): thread t sums column t % 64
+            // over rows (t / 64) * 64 .. + 63 and adds it to colsum[gcol] -- replaces a separate pass over the output.
+            // The buffer is rewritten two items later, behind a named barrier every thread passes after these reads.
+            const uint32_t gt = epi_tid & 127u;
+            const int c = int(gt & 63u), r0 = int(gt >> 6) * 64;
+            const uint32_t chunk = uint32_t(c) >> 3, within = (uint32_t(c) & 7u) * 2u;
+            float accs = 0.f;
+#pragma unroll 8
+            for (int r = r0; r < r0 + 64; ++r) {
+              if (m0 + r < p.M)
+                accs += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(buf + r * 128 + ((chunk ^ (uint32_t(r) & 7u)) << 4) + within));
+            }
+            if (gcol0 + c < p.N) atomicAdd(p.colsum + gcol0 + c, accs);
+            // aux mode: the issuer TMA-loads the aux slab of item i+2 into THIS buffer right after the next TMEM read, with
+            // no group barrier in between -> every thread must be done reading it first
+            if (has_aux) named_bar_sync(bar_id, 128);
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -586,7 +605,8 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
 static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                      int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                      float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2, void* b_persist,
-                     int ldbp, const float* scale_a, const float* scale_b, const void* rng, int drop_stream, float drop_p) {
+                     int ldbp, const float* scale_a, const float* scale_b, const void* rng, int drop_stream, float drop_p,
+                     float* colsum) {
   using namespace dtb;
   const int KBLK = 128 / esz;  // K elements per 128-byte swizzle atom
   if (esz == 1 && (a_mn || b_mn || b2 || b_persist)) return 2002;  // fp8 path: K-major operands only
@@ -645,6 +665,8 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
   p.drop.thr = (rng && drop_p > 0.f) ? uint32_t(drop_p * 65536.f + 0.5f) : 0u;
   p.drop.scale = 1.f / (1.f - drop_p);
   if (p.drop.thr && ((N & 1) || !(epi == EPI_BIAS_RESID || epi == EPI_RESID))) return 2003;
+  p.colsum = colsum;
+  if (colsum && (out_f32 || epi == EPI_BIAS_GELU)) return 2004;
   const int tiles_mg = (p.tiles_m + CL - 1) / CL;
   int total = tiles_mg * p.tiles_n * p.splits;   // work items per cluster
   int max_clusters = num_sms / CL;
@@ -659,14 +681,14 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
 extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                              int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                              float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,
-                             void* b_persist, int ldbp, const void* rng, int drop_stream, float drop_p) {
+                             void* b_persist, int ldbp, const void* rng, int drop_stream, float drop_p, float* colsum) {
   return gemm_impl(2, a, b, c, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_f32, epi, bias, aux, ldaux, c2, ldc2, alpha, splits, num_sms,
-                   stream, b2, ldb2, b_persist, ldbp, nullptr, nullptr, rng, drop_stream, drop_p);
+                   stream, b2, ldb2, b_persist, ldbp, nullptr, nullptr, rng, drop_stream, drop_p, colsum);
 }
 extern "C" int dtb_gemm_fp8(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int epi,
                             const void* bias, const void* aux, int ldaux, void* c2, int ldc2, float alpha, int num_sms,
                             cudaStream_t stream, const float* scale_a, const float* scale_b, const void* rng, int drop_stream,
                             float drop_p) {
   return gemm_impl(1, a, b, c, M, N, K, lda, ldb, ldc, 0, 0, 0, epi, bias, aux, ldaux, c2, ldc2, alpha, 1, num_sms, stream, nullptr, 0,
-                   nullptr, 0, scale_a, scale_b, rng, drop_stream, drop_p);
+                   nullptr, 0, scale_a, scale_b, rng, drop_stream, drop_p, nullptr);
 }

@@ -530,6 +530,8 @@ class TransformerEngine:
             ops.gemm(self.du, Lp.fc_w, self.dh, b_mn=True)
             ops.gemm(self.du, self.h2[l], Lg.fc_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.fc_b is not None:
+                # (folding this column sum into the dgelu GEMM's epilogue -- ops.gemm(colsum_out=...) -- was measured slower:
+                # +36 us per GEMM for the smem column pass vs the 21 us of this separate launch)
                 ops.colsum(self.du, Lg.fc_b)
             self._norm_bwd(self.dh, self.xmid[l], Lp.ln2_w, self.mean2[l], self.rstd2[l], dx2, Lg.ln2_w, Lg.ln2_b, dx, Lg.o_b,
                            dm2, self._drop("resid1", l))
@@ -539,14 +541,13 @@ class TransformerEngine:
             # ---- attention block ----
             ops.gemm(dy, Lp.o_w, self.datt, b_mn=True)
             ops.gemm(dy, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
+            # d(qkv bias) = colsum(dqkv) rides on the attention backward (GPT-2 has no RoPE between the two)
             ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv,
-                              drop=self._drop("attn", l))
+                              drop=self._drop("attn", l), dbias=Lg.qkv_b)
             if cfg.family == "llama":
                 ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
             ops.gemm(self.dqkv, Lp.qkv_w, self.dh, b_mn=True)
             ops.gemm(self.dqkv, self.h1[l], Lg.qkv_w, a_mn=True, b_mn=True, accumulate=True)
-            if Lg.qkv_b is not None:
-                ops.colsum(self.dqkv, Lg.qkv_b)
             nxt = l - 1
             self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx,
                            G.layers[nxt].proj_b if nxt >= 0 else None, dm2 if nxt >= 0 else None,

@@ -73,7 +73,7 @@ def _row_major(t: torch.Tensor, what: str) -> int:
 # GEMM
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=0, b2=None, b_persist=None, drop=None):
+         splits=0, b2=None, b_persist=None, drop=None, colsum_out=None):
     """out[M,N] = epi(alpha * A @ B^T) -- see :func:`reference.gemm` for the operand conventions.
 
     CUDA: persistent tcgen05/TMEM/TMA kernel (csrc/sm100_gemm.cu).  fp32 ``out`` is always reduce-ADDED by TMA
@@ -84,10 +84,15 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     ``b_persist``: local destination of the same shape as ``b`` -- when ``b`` is read from a PEER window (fused
     broadcast -> first forward GEMM) every B tile is also TMA-stored there while the MMA consumes it.
     ``drop`` (``Drop``, residual epilogues only): ``out = aux + dropout(alpha A B^T + bias)``, mask generated in the epilogue.
+    ``colsum_out`` (fp32 [N], bf16 outputs): += column sums of ``out`` from the epilogue's staged tiles (a bias gradient that
+    equals colsum of this GEMM's output, without a second pass over it).
     """
     if not use_kernels(out):
-        return ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
-                        accumulate=accumulate, b2=b2, b_persist=b_persist, drop=drop)
+        ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
+                 accumulate=accumulate, b2=b2, b_persist=b_persist, drop=drop)
+        if colsum_out is not None:
+            ref.colsum(out, colsum_out)
+        return out
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb, ldc = _row_major(a, "a"), _row_major(b, "b"), _row_major(out, "out")
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -112,7 +117,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
         _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), int(out_f32), EPI[epi],
         _lib.ptr(bias), _lib.ptr(aux), ldaux, _lib.ptr(out2), ldc2, ctypes.c_float(alpha), splits, _lib.num_sms(),
         _lib.stream_ptr(), _lib.ptr(b2), _row_major(b2, "b2") if b2 is not None else 0, _lib.ptr(b_persist),
-        _row_major(b_persist, "b_persist") if b_persist is not None else 0, *_drop_args(drop))
+        _row_major(b_persist, "b_persist") if b_persist is not None else 0, *_drop_args(drop), _lib.ptr(colsum_out))
     _c(rc, "gemm")
     _tick()
     return out
@@ -308,9 +313,9 @@ def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
     return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop)
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None, dbias=None):
     from . import attention as _att
-    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop)
+    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop, dbias)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ def run_case(idx: int) -> dict:
         rc = L.dtb_gemm_bf16(
             _lib.ptr(A_st), _lib.ptr(B_st), _lib.ptr(C), M, N, K, lda, ldb, ldc, a_mn, b_mn, out_f32, epi,
             _lib.ptr(bias), _lib.ptr(aux), ldc, _lib.ptr(C2), ldc, ctypes.c_float(1.0), splits, _lib.num_sms(),
-            _lib.stream_ptr(), None, 0, None, 0, None, 0, ctypes.c_float(0.0))
+            _lib.stream_ptr(), None, 0, None, 0, None, 0, ctypes.c_float(0.0), None)
         assert rc == 0, rc
 
     call()

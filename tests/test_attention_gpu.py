@@ -25,7 +25,11 @@ def test_attention_fwd_bwd(B, T, H, Hkv):
     assert (lse - r_lse).abs().max().item() < 2e-2
     dout = (torch.randn(M, H * hd, device="cuda") * 0.5).bfloat16()
     dqkv = torch.zeros_like(qkv)
-    ops.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv)
+    dbias = torch.zeros((H + 2 * Hkv) * hd, device="cuda")
+    ops.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, dbias=dbias)
+    # qkv bias gradient (folded into the single-block kernel, separate colsum otherwise) = column sums of the stored dqkv
+    want = dqkv.float().sum(0)
+    assert (dbias - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
     r_dqkv = torch.empty(M, (H + 2 * Hkv) * hd, device="cuda")
     ref.attention_bwd(dout, qkv, r_out.bfloat16(), r_lse, r_dqkv, B, T, H, hd, Hkv)
     names = ["dq", "dk", "dv"]

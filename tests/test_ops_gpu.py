@@ -376,3 +376,19 @@ def test_layernorm_bwd_masked_copy_and_bias_fold(d):
             want = dx.float() * ref.drop_mult_2d(rng.state, 7, 0.1, M, d, DEV)
             _close(dxm, want, rtol=1e-2)
             _close(dcol, want.sum(0), rtol=5e-3)
+
+
+def test_gemm_colsum_fold():
+    """Bias gradient folded into the producing GEMM's epilogue == column sums of the stored bf16 output."""
+    torch.manual_seed(13)
+    M, N = 1000, 3072  # dY [M, 768] x W [768, 3072] (B MN-major) -> du [M, 3072], as in the MLP backward
+    a, w, u = _bf(M, 768), _bf(768, N, scale=0.05), _bf(M, N)
+    out, r = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm(a, w, out, b_mn=True, epi="dgelu", aux=u, colsum_out=cs)
+    ref.gemm(a, w, r, b_mn=True, epi="dgelu", aux=u)
+    _close(out, r)
+    _close(cs, out.float().sum(0), rtol=1e-4)
+    cs2 = torch.zeros(N, device=DEV)
+    ops.gemm(a, w, out, b_mn=True, colsum_out=cs2)   # plain epilogue, no aux
+    _close(cs2, out.float().sum(0), rtol=1e-4)
