@@ -117,7 +117,6 @@ __global__ void embed_bwd_kernel(const bf16* __restrict__ dx, const int* __restr
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm / RMSNorm: one warp per row, the row (<= 8192 elements) is held in registers between the passes.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kMaxVecPerLane = 32;  // supports d up to 32*32*8 = 8192
 
 template <bool RMS>
 __global__ void __launch_bounds__(256) norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,

@@ -234,18 +234,18 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     tc_fence_before();  // order this iteration's TMEM reads before the next iteration's MMA writes
     __syncthreads();
   }
-  // ---- epilogue ----
-  if (row_tok < p.M) {
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* dst = p.out + size_t(row_tok) * p.ld_out + h * kHd;
+  // ---- epilogue: O tile staged (swizzled) in the Q tile -- every MMA that read it has completed -- and stored by TMA ----
+  {
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;  // rows >= M: all masked -> zeros, clipped by the tensor map anyway
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
       uint4 q;
       q.x = pack2(acc[v * 8 + 0] * inv, acc[v * 8 + 1] * inv); q.y = pack2(acc[v * 8 + 2] * inv, acc[v * 8 + 3] * inv);
       q.z = pack2(acc[v * 8 + 4] * inv, acc[v * 8 + 5] * inv); q.w = pack2(acc[v * 8 + 6] * inv, acc[v * 8 + 7] * inv);
-      reinterpret_cast<uint4*>(dst)[v] = q;
+      st_swz(sQ, tid, v, q);
     }
-    if (p.lse) {
+    fence_proxy_async_smem();
+    if (row_tok < p.M && p.lse) {
       const int b = row_tok / p.T, t = row_tok % p.T;
       p.lse[(size_t(b) * p.H + h) * p.T + t] = (m_run + log2f(l_run)) * 0.6931471805599453f;
     }
@@ -253,6 +253,12 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    if (elect_one()) {
+      tma_store_2d(&p.tmap_out, sQ, h * kHd, q0);
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
