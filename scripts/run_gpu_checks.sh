@@ -1,11 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_ops_gpu.py tests/test_engine.py -x -q -m gpu 2>&1 | tail -3
-for i in 1 2; do
-timeout 200 python scripts/step_bench.py --batch 256 --steps 30 2>&1 | tail -1 | cut -c1-150
-(cd gpurun_tmp/base && timeout 200 python scripts/step_bench.py --batch 256 --steps 30 2>&1 | tail -1 | cut -c1-150)
-done
-timeout 200 python scripts/step_bench.py --batch 512 --steps 20 2>&1 | tail -1 | cut -c1-150
-(cd gpurun_tmp/base && timeout 200 python scripts/step_bench.py --batch 512 --steps 20 2>&1 | tail -1 | cut -c1-150)
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_v10.csv python scripts/step_bench.py --batch 256 --steps 1 --warmup 1 --no-graph > gpurun_out/ncu_c.log 2>&1
-python scripts/kernel_shares.py gpurun_out/launches_v10.csv > gpurun_out/kernel_shares_v10.json; grep -E '"kernel"|total_us' gpurun_out/kernel_shares_v10.json | head -20
+timeout 600 python -m pytest tests/test_multigpu.py -x -q -m gpu 2>&1 | tail -4
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --steps 30 --warmup 5 2>&1 | grep -E '^\{|rror' | tee gpurun_out/bench_n2_final.jsonl | cut -c1-1700
