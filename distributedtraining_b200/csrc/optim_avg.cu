@@ -550,6 +550,48 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int n, int stride, uint
 }  // namespace dtb
 
 using namespace dtb;
+
+// ------------------------------------------------------------------------------------------------------------------
+// NVLS path: in-switch reduction + multicast broadcast (NVSwitch SHARP) for the UNIFORM / pre-scaled mixers.
+//   every rank owns one contiguous shard of the arena and, for it,
+//     sum   = multimem.ld_reduce.add(delta_mc)      -- ONE load returns sum_i delta_i: the switch pulls the N copies
+//     theta = base_scale * base + scale * sum
+//     multimem.st(out_mc, theta)                    -- ONE store lands in every rank's landing buffer
+// so a rank receives |arena| / N reduced bytes and |arena| (N-1)/N broadcast bytes, half the ingress of the pull round
+// (which reads N-1 full shards twice), and issues no per-peer loop at all.  delta_mc / out_mc are MULTICAST addresses of
+// symmetric allocations (torch.distributed._symmetric_memory: cuMulticast objects), base is this rank's local copy.
+// Replaces the reference's N downloads + N x 148 ATen axpys (hivetrain/averaging_logic.py:431-448) for mixers that
+// do not need per-miner weights learned on the averager.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__global__ void __launch_bounds__(256) nvls_avg_kernel(const float* __restrict__ delta_mc, float* __restrict__ out_mc,
+                                                       const float* __restrict__ base, size_t lo4, size_t hi4, size_t base4,
+                                                       float scale, float base_scale) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = lo4 + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+    // the symmetric buffers are padded to a multiple of the world size; the local base copy is not
+    const float4 b = i < base4 ? __ldg(reinterpret_cast<const float4*>(base) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 sum = multimem_ld_reduce_add(delta_mc + 4 * i);
+    float4 o;
+    o.x = fmaf(base_scale, b.x, scale * sum.x);
+    o.y = fmaf(base_scale, b.y, scale * sum.y);
+    o.z = fmaf(base_scale, b.z, scale * sum.z);
+    o.w = fmaf(base_scale, b.w, scale * sum.w);
+    multimem_st(out_mc + 4 * i, o);
+  }
+}
+
 #define KCHECK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
 extern "C" int dtb_adam_prep(int* step, float* hyper, cudaStream_t s) {
@@ -665,6 +707,14 @@ extern "C" int dtb_shard_pull_reset(const float** shard_src, const uint32_t** wa
   p.reset_moments = reset_moments; p.wait_value = wait_flags ? wait_value : 0;
   if (grid > num_chunks) grid = num_chunks;
   shard_pull_reset_kernel<<<grid, 256, 0, s>>>(p);
+  return KCHECK();
+}
+
+// delta_mc / out_mc: multicast addresses; [lo4, hi4): this rank's shard in units of float4
+extern "C" int dtb_nvls_avg(const float* delta_mc, float* out_mc, const float* base, size_t lo4, size_t hi4, size_t base4,
+                            float scale, float base_scale, int grid, cudaStream_t s) {
+  if (hi4 <= lo4) return 0;
+  nvls_avg_kernel<<<grid, 256, 0, s>>>(delta_mc, out_mc, base, lo4, hi4, base4, scale, base_scale);
   return KCHECK();
 }
 

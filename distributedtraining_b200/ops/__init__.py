@@ -533,6 +533,18 @@ def shard_pull_reset(shard_ptrs, manifest, chunks_per_rank, base_out, master, p1
     _tick()
 
 
+def nvls_avg(delta_mc: int, out_mc: int, base: torch.Tensor, lo4: int, hi4: int, scale: float, base_scale: float = 1.0) -> None:
+    """NVLS (in-switch) reduce + multicast broadcast of this rank's shard [lo4, hi4) (float4 units):
+    ``out_all_ranks = base_scale * base + scale * sum_ranks(delta)``.  ``delta_mc`` / ``out_mc`` are multicast addresses
+    of symmetric allocations (parallel.exchange.NvlsExchange); csrc/optim_avg.cu: nvls_avg_kernel."""
+    assert use_kernels(base), "nvls_avg is an NVSwitch op (CUDA only)"
+    assert base.numel() % 4 == 0 and base.dtype == torch.float32
+    _c(_lib.lib().dtb_nvls_avg(ctypes.c_void_p(delta_mc), ctypes.c_void_p(out_mc), _lib.ptr(base), ctypes.c_size_t(lo4),
+                               ctypes.c_size_t(hi4), ctypes.c_size_t(base.numel() // 4), ctypes.c_float(scale),
+                               ctypes.c_float(base_scale), _lib.num_sms() * 8, _lib.stream_ptr()), "nvls_avg")
+    _tick()
+
+
 def checksum(flat: torch.Tensor) -> str:
     """Order-independent 128-bit device checksum of a flat fp32/bf16 arena (hex string).  CPU: same arithmetic in torch."""
     words = flat.contiguous().view(torch.int32)

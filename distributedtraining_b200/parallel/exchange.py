@@ -3,6 +3,8 @@
 =============  =====================================================================================================
 ``peer``       one-sided symmetric windows over NVLink/NVSwitch; the averaging is ONE fused kernel that pulls peer
                deltas, applies the learned weights, adds the base and pushes the result (csrc/optim_avg.cu).
+``nvls``       uniform / pre-scaled mixers: ONE kernel per rank reduces its shard inside the NVSwitch (``multimem.ld_reduce``) and
+               multicasts the new base to every rank (``multimem.st``) -- no per-peer loop, half the ingress of ``peer``.
 ``collective`` ``all_gather`` + torch weighted sum + ``broadcast`` over a process group (NCCL = the reference-style
                baseline this framework must beat; gloo = CPU plumbing).
 ``disk``       files in a shared directory (the analogue of the reference's ``LocalHFManager`` /
@@ -334,3 +336,56 @@ class PeerExchange(Exchange):
     def fetch_base(self, out: torch.Tensor) -> int:
         out.copy_(self.base_view())
         return self.base_round()
+
+
+class NvlsExchange(Exchange):
+    """Uniform / pre-scaled averaging through NVSwitch multicast objects (NVLS).
+
+    One symmetric allocation per rank (``torch.distributed._symmetric_memory``: CUDA VMM + ``cuMulticast*``) holds this
+    rank's fp32 delta and the landing buffer of the new base.  A round is: emit the delta locally -> device barrier ->
+    ``nvls_avg`` on this rank's shard (``multimem.ld_reduce`` sums the N deltas in the switch, ``multimem.st`` lands the
+    result on every rank) -> device barrier -> local optimizer reset from the landing buffer.
+    The learned per-(miner, tensor) mixer needs the individual deltas on the averager and keeps using ``PeerExchange``;
+    this plane serves ``--mixer uniform`` (reference DeltaAverager with equal weights, averaging_logic.py:200-269).
+    """
+
+    name = "nvls"
+
+    def __init__(self, manifest: Manifest, group=None, device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        assert dist.is_initialized() and torch.cuda.is_available()
+        self.man = manifest
+        self.group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        n = manifest.total
+        quantum = 4 * self.world * 32                      # float4 shards, 32 float4 per warp-row
+        self.n, self.npad = n, (n + quantum - 1) // quantum * quantum
+        self.buf = symm_mem.empty(2 * self.npad, dtype=torch.float32, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
+        if not self.handle.multicast_ptr:
+            raise RuntimeError("this system exposes no NVLS multicast object (multicast_ptr == 0)")
+        self.buf.zero_()
+        self.delta = self.buf[:self.npad]
+        self.landing = self.buf[self.npad:]
+        self.mc_delta = int(self.handle.multicast_ptr)
+        self.mc_landing = self.mc_delta + 4 * self.npad
+        per4 = self.npad // 4 // self.world
+        self.lo4, self.hi4 = self.rank * per4, (self.rank + 1) * per4
+        self.handle.barrier()
+        self._round = 0
+
+    def publish_delta(self, trainer, round: int) -> None:
+        trainer.emit_delta(self.delta[:self.n])
+
+    def average_broadcast(self, base: torch.Tensor, scale: Optional[float] = None, base_scale: float = 1.0) -> torch.Tensor:
+        """new_base (on EVERY rank, in ``self.landing``) = base_scale * base + scale * sum_i delta_i; default scale 1/N."""
+        self.handle.barrier()  # every rank's delta is complete and visible
+        ops.nvls_avg(self.mc_delta, self.mc_landing, base, self.lo4, self.hi4, scale if scale is not None else 1.0 / self.world,
+                     base_scale)
+        self.handle.barrier()  # every shard has landed everywhere
+        self._round += 1
+        return self.landing[:self.n]
+
+    def delta_round(self, src: int) -> int:
+        return self._round

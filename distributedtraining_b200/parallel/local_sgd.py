@@ -117,6 +117,12 @@ class LocalSGDCoordinator:
                     t.opt.set_lr(self.post_pull_lr)
                 return
             new_base = self.ex.sharded_average_broadcast(t.base, self.w, r, self.miners)
+        elif getattr(self.ex, "name", "") == "nvls":
+            # uniform mixer on the NVLS plane: in-switch sum of the deltas + multicast of the new base (1 kernel per rank)
+            with self.timer.phase("delta_emit"):
+                self.ex.publish_delta(t, r)
+            with self.timer.phase("gather_avg"):
+                new_base = self.ex.average_broadcast(t.base)
         elif isinstance(self.ex, CollectiveExchange):
             if self.mixer == "learned" and self.meta_steps > 0 and self.val_batches:
                 self._meta_learn_collective()

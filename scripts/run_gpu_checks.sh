@@ -1,10 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_engine.py -x -q -m gpu 2>&1 | tail -3
-for i in 1 2; do
-timeout 200 python scripts/step_bench.py --batch 256 --steps 30 2>&1 | tail -1 | cut -c1-150
-(cd gpurun_tmp/base && timeout 200 python scripts/step_bench.py --batch 256 --steps 30 2>&1 | tail -1 | cut -c1-150)
-done
-timeout 200 python scripts/step_bench.py --batch 512 --steps 20 2>&1 | tail -1 | cut -c1-150
-(cd gpurun_tmp/base && timeout 200 python scripts/step_bench.py --batch 512 --steps 20 2>&1 | tail -1 | cut -c1-150)
-timeout 200 python scripts/gemm_check.py --only perf_ 2>&1 | cut -c1-260
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 scripts/nvls_check.py 2>&1 | grep -E "NVLS_CHECK|rror|Traceback|File " | cut -c1-1200 | tail -12
