@@ -36,7 +36,7 @@ def parse_args(argv=None):
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl", "nvls"])
     ap.add_argument("--model", type=str, default="gpt2")
     ap.add_argument("--batch-size", type=int, default=512, help="sequences per miner per step (both arms use the same default)")
     ap.add_argument("--seq-len", type=int, default=64, help="reference miner sequence length (neurons/miner.py:70)")
@@ -132,13 +132,18 @@ def run_ours(args) -> dict:
     if args.impl == "nccl":
         ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
         plane = "nccl all_gather + torch weighted sum" if world > 1 else "local torch"
+    elif args.impl == "nvls" and world > 1:
+        from distributedtraining_b200.parallel.exchange import NvlsExchange
+        ex = NvlsExchange(trainer.man)  # uniform mixer: in-switch reduction + multicast of the new base
+        plane = "NVLS (multimem.ld_reduce + multimem.st), uniform mixer"
+        args.meta_steps = 0
     else:
         ex = PeerExchange(trainer.man, delta_dtype=args.delta_dtype)
         plane = "peer windows (fused gather-avg-broadcast kernel)"
     dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
     host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
     val = SyntheticTokens(B, T, V, seed=7, device=str(device), pool=2)
-    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps,
+    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps, mixer="uniform" if args.impl == "nvls" else "learned",
                                 val_batches=[b["input_ids"] for b in val.pool], post_pull_lr=5e-5)
     # the optimizer keeps lr=5e-4 in round 0 and 5e-5 after the first pull, as in the reference miner
 

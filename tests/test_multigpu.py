@@ -38,3 +38,19 @@ def test_bench_two_gpus_runs():
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])
     assert out["n_gpus"] == 2 and out["value"] > 0 and out["rounds_in_timed_region"] >= 2 and out["e2e"]["value"] > 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_nvls_plane_matches_allreduce_reference():
+    """In-switch reduction + multicast broadcast (multimem.*) == fp32 all-reduce reference; skipped where the box exposes no
+    multicast object."""
+    n = min(_ngpu(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "scripts", "nvls_check.py"), "--mb", "16"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("NVLS_CHECK ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(line[-1][len("NVLS_CHECK "):])
+    if "nvls" in out:
+        pytest.skip(out["nvls"])
+    assert out["all_ranks_ok"], out
