@@ -1,3 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29571 scripts/nvls_check.py 2>&1 | grep -E "NVLS_CHECK|rror|Traceback|File " | cut -c1-1200 | tail -12
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
+timeout 400 python bench.py --gpus 1 --steps 40 --warmup 5 2>&1 | grep -E '^\{|rror' | tee gpurun_out/bench_n1_final.jsonl | cut -c1-1800
