@@ -222,6 +222,12 @@ class ParameterizedAverager(DeltaAverager):
             self.miner_hotkeys.append(hotkey)
             if self.cache_to_disk:
                 self.store_weight_delta(flat, hotkey)
+        ex = getattr(self.hf_manager, "exchange", None)
+        if hasattr(ex, "stale_miners"):  # peer plane: name the ranks whose heartbeat lags behind the averaging round
+            self._avg_round = getattr(self, "_avg_round", 0) + 1
+            stale = ex.stale_miners(self._avg_round)
+            if stale:
+                logger.warning(f"averaging round {self._avg_round}: ranks {stale} have not published (skipped)")
         return len(self.deltas)
 
     @property

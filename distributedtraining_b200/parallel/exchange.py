@@ -232,9 +232,16 @@ class PeerExchange(Exchange):
         """Delta is written straight into this rank's window (no copies), then the round flag is release-stored."""
         trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round))
         self.win.publish(self.F_DELTA, round, dst_ranks)
+        self.win.heartbeat()  # liveness counter next to the round flag (failure detection, SURVEY 5.3)
 
     def delta_round(self, src: int) -> int:
         return int(self.win.flags()[self.F_DELTA + src].item())
+
+    def stale_miners(self, min_beat: int, miners: Optional[Sequence[int]] = None) -> List[int]:
+        """Miners that published fewer than ``min_beat`` deltas so far (dead, stalled or late): the averager treats them
+        like the reference treats a failed download -- skipped for the round -- and logs them."""
+        stale = set(self.win.stale_ranks(min_beat))
+        return [r for r in (range(self.world) if miners is None else miners) if r in stale]
 
     def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
         latest = int(self.win.flags()[self.F_DELTA + src].item())
