@@ -198,6 +198,14 @@ def run_ours(args) -> dict:
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},
     }
+    # avg-round wall time (BASELINE.json's second metric) for the configured cadence: local_steps optimizer steps + one
+    # exchange; measured directly when the timed region spans whole rounds, projected from the per-step and per-exchange
+    # device times otherwise (a short K with one forced round)
+    exch_ms = sum(phases.values()) / max(rounds, 1)
+    step_ms = (ms_total - exch_ms * rounds) / K
+    result["round_ms_at_local_steps"] = {"local_steps": args.local_steps, "exchange_ms": round(exch_ms, 3),
+                                         "step_ms": round(step_ms, 3), "round_ms": round(args.local_steps * step_ms + exch_ms, 2),
+                                         "measured_directly": bool(K % args.local_steps == 0 and K >= args.local_steps)}
     # ---- region 2: end to end through the public API (pinned-host inputs, per-step loss read-back) ----
     if not args.no_e2e:
         loop = DeltaLoop(device, args.model, host_data, learning_rate=args.lr, hf_manager=None, trainer=trainer,
