@@ -1,0 +1,95 @@
+"""Property tests (hypothesis) of the layout / algebra invariants every plane relies on.  CPU only."""
+import math
+
+import torch
+from hypothesis import given, settings, strategies as st
+
+from distributedtraining_b200 import ops
+from distributedtraining_b200.models.arena import ALIGN, CHUNK, Manifest
+from distributedtraining_b200.ops import reference as ref
+from distributedtraining_b200.parallel.launch import parse_roles
+
+shapes = st.lists(st.tuples(st.integers(1, 70), st.integers(1, 40)), min_size=1, max_size=7)
+
+
+@settings(max_examples=40, deadline=None)
+@given(shapes)
+def test_manifest_layout_invariants(shs):
+    man = Manifest([(f"t{i}", s, "normal", True) for i, s in enumerate(shs)])
+    flat = torch.arange(man.total, dtype=torch.float32)
+    seen = torch.zeros(man.total, dtype=torch.int32)
+    for s in man:
+        assert s.offset % ALIGN == 0 and man.view(flat, s.name).shape == s.shape
+        seen[s.offset:s.offset + s.numel] += 1
+    assert int(seen.max()) == 1 and int(seen.sum()) == man.num_params          # views never overlap
+    cs, cl, ct = man.seg_table("cpu")
+    assert int(cl.sum()) == man.total and int(cl.max()) <= CHUNK                # chunks tile the arena exactly ...
+    tid = man.tensor_ids("cpu")
+    for c in range(cs.numel()):                                                  # ... and never straddle two tensors
+        seg = tid[int(cs[c]):int(cs[c]) + int(cl[c])]
+        assert int(seg.min()) == int(seg.max()) == int(ct[c])
+    assert man.same_layout({s.name: s.shape for s in man}) and not man.same_layout({s.name: (1,) for s in man})
+
+
+@settings(max_examples=25, deadline=None)
+@given(shapes, st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+def test_weighted_average_identity(shs, n_miners, seed):
+    """theta_bar = s_j * base + sum_i w_ij * delta_ij  ==  sum_i w_ij * (base + delta_ij)   (SURVEY 2.6-C.2), and the
+    meta-gradient dots G_ij = <g_j, base_j + delta_ij - theta_bar_j> match the per-tensor definition."""
+    g = torch.Generator().manual_seed(seed)
+    man = Manifest([(f"t{i}", s, "normal", True) for i, s in enumerate(shs)])
+    P = len(man)
+    valid = torch.zeros(man.total)
+    for s in man:                                    # arenas keep their alignment padding at zero (init, AdamW, emit)
+        valid[s.offset:s.offset + s.numel] = 1.0
+    base = torch.randn(man.total, generator=g) * valid
+    deltas = [0.1 * torch.randn(man.total, generator=g) * valid for _ in range(n_miners)]
+    w = torch.rand(n_miners, P, generator=g)
+    out = torch.empty(man.total)
+    ops.weighted_avg(base, deltas, w, man, [out])
+    grad = torch.randn(man.total, generator=g) * valid
+    G = torch.empty(n_miners, P)
+    ops.multi_dot(grad, deltas, base, out, man, G)
+    for j, s in enumerate(man):
+        want = sum(w[i, j] * (man.view(base, j) + man.view(deltas[i], j)) for i in range(n_miners))
+        assert torch.allclose(man.view(out, j), want, atol=1e-5)
+        for i in range(n_miners):
+            gij = (man.view(grad, j) * (man.view(base, j) + man.view(deltas[i], j) - man.view(out, j))).sum()
+            assert math.isclose(float(G[i, j]), float(gij), rel_tol=1e-3, abs_tol=1e-3)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 64), st.integers(0, 2 ** 31 - 1))
+def test_block_fp8_delta_roundtrip_error_bound(nblocks, seed):
+    g = torch.Generator().manual_seed(seed)
+    n = 32 * nblocks
+    base = torch.randn(n, generator=g)
+    master = base + torch.randn(n, generator=g) * torch.rand(1, generator=g) * 0.1
+    q, sc = torch.empty(n, dtype=torch.uint8), torch.empty(nblocks)
+    ops.delta_emit(master, base, q, sc)
+    back = ops.dequant_fp8(q, sc)
+    d = master - base
+    amax = d.view(-1, 32).abs().amax(1, keepdim=True).expand(-1, 32).reshape(-1)
+    assert bool(((back - d).abs() <= amax / 16 + 1e-12).all())       # e4m3: 3 mantissa bits -> half-ulp <= amax / 16 per block
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(0, 1000), st.integers(0, 50), st.floats(0.01, 0.5))
+def test_dropout_mask_is_a_pure_function_with_the_right_rate(seed, counter, stream, p):
+    m1 = ref.drop_mult_2d((seed, counter), stream, p, 64, 128, "cpu")
+    m2 = ref.drop_mult_2d((seed, counter), stream, p, 64, 128, "cpu")
+    assert torch.equal(m1, m2)
+    vals = set(m1.unique().tolist())
+    assert vals <= {0.0, float(torch.tensor(1.0 / (1.0 - p), dtype=torch.float32))}
+    keep = (m1 > 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.03                                 # 8192 Bernoulli draws: 3 sigma < 0.017
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 16))
+def test_parse_roles_covers_requested_ranks(world):
+    roles = parse_roles(f"miner:0-{world - 1}", world)
+    assert roles["miner"] == list(range(world))
+    if world >= 3:
+        r = parse_roles(f"miner:0-{world - 3},validator:{world - 2},averager:{world - 1}", world)
+        assert r["validator"] == [world - 2] and r["averager"] == [world - 1] and len(r["miner"]) == world - 2
