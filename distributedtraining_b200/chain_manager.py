@@ -9,7 +9,6 @@ from __future__ import annotations
 import json
 import multiprocessing as mp
 import os
-import pickle
 from typing import Any, Callable, Optional
 
 from .utils.logging import logger

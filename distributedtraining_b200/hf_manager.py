@@ -13,9 +13,7 @@ The same method names are served by an :class:`~distributedtraining_b200.paralle
 """
 from __future__ import annotations
 
-import hashlib
 import os
-import shutil
 from typing import Dict, Optional, Union
 
 import torch

@@ -7,14 +7,14 @@ flat-arena op of the framework (delta emit, fused weighted average, multi-dot, f
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from typing import Callable, Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .arena import Arena, Manifest
+from .arena import Manifest
 
 
 class FeedforwardNN(nn.Module):

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from .. import ops
-from .arena import Arena, Manifest
+from .arena import Manifest
 from .transformer import ModelConfig, TransformerEngine, build_manifest, get_config, new_model
 
 

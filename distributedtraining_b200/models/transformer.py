@@ -16,7 +16,7 @@ i.e. transposed w.r.t. HF GPT-2's Conv1D -- :func:`to_hf_state_dict` converts.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch

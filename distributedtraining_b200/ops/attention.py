@@ -7,7 +7,6 @@ from __future__ import annotations
 import ctypes
 import math
 
-import torch
 
 from . import _lib, reference as ref
 

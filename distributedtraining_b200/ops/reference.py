@@ -6,7 +6,7 @@ All functions write into caller-provided output buffers so the engine code path 
 from __future__ import annotations
 
 import math
-from typing import Optional, Sequence
+from typing import Sequence
 
 import torch
 import torch.nn.functional as F

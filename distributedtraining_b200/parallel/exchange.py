@@ -16,10 +16,8 @@ All planes move *flat arenas* (see models/arena.py), never ``dict[str, Tensor]``
 from __future__ import annotations
 
 import hashlib
-import json
 import os
-import time
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist

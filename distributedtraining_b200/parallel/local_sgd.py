@@ -16,13 +16,12 @@ Reference semantics: miners hivetrain/training_manager.py:345-433, averager hive
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
 
 from .. import ops
-from ..utils.logging import logger
 from ..utils.tracing import PhaseTimer
 from .exchange import CollectiveExchange, PeerExchange
 

@@ -22,7 +22,7 @@ from typing import Callable, Dict, Iterable, Optional
 
 import torch
 
-from . import ops
+from . import ops  # noqa: F401  (re-exported: callers reach the op layer through this module as upstream scripts did)
 from .config.mlflow_config import MLFLOW_ACTIVE
 from .models.toys import FeedforwardNN, ModuleTrainer, SimpleCNN  # noqa: F401  (re-exported like the reference)
 from .models.trainer import Trainer

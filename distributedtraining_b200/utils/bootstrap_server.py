@@ -11,7 +11,7 @@ import json
 import threading
 import time
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
-from typing import Dict, Optional
+from typing import Dict
 from urllib.parse import parse_qs, urlparse
 
 from .logging import logger

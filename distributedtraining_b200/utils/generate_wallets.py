@@ -6,7 +6,7 @@ from __future__ import annotations
 import json
 import os
 import secrets
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 
 def generate_multiple_wallets(n: int, path: str = "~/.dtb200/wallets", prefix: str = "test", ledger=None, stake: float = 10.0,

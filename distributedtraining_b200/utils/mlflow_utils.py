@@ -6,7 +6,6 @@ when inactive, metrics go to the JSONL logger only.  The system-metric helpers a
 from __future__ import annotations
 
 import os
-import time
 from typing import Dict, Optional
 
 import torch

@@ -6,7 +6,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from distributedtraining_b200.averaging_logic import DeltaAverager, GeneticAverager, ParameterizedAverager  # noqa: E402
+from distributedtraining_b200.averaging_logic import GeneticAverager, ParameterizedAverager  # noqa: E402
 from distributedtraining_b200.data import SyntheticTokens  # noqa: E402
 from distributedtraining_b200.models.trainer import Trainer  # noqa: E402
 from distributedtraining_b200.runtime import build_context  # noqa: E402
