@@ -165,9 +165,11 @@ class CollectiveExchange(Exchange):
         dist.all_gather_into_tensor(self._gathered.view(-1), mine, group=self.group)
         return self._gathered
 
-    def allgather_average(self, trainer, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        """The NCCL(+ATen) baseline of fused kernel (a): all_gather, then N weighted axpys + base add."""
-        g = self.allgather_deltas(trainer)
+    def allgather_average(self, trainer, w: torch.Tensor, out: torch.Tensor, gathered: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The NCCL(+ATen) baseline of fused kernel (a): all_gather, then N weighted axpys + base add.  ``gathered``: the
+        deltas of THIS round if they were already collected (the learned mixer overwrites the averager's master copy while
+        it evaluates candidate averages, so the delta must not be re-emitted afterwards)."""
+        g = gathered if gathered is not None else self.allgather_deltas(trainer)
         tid = self.man.tensor_ids(out.device)
         _torch_weighted_avg(trainer.base, g, w, tid, out)
         self._round += 1

@@ -62,10 +62,10 @@ class LocalSGDCoordinator:
                           mode={"fp32": 0, "bf16": 1, "fp8": 2}[ex.delta_dtype_name])
             self.w.add_(self._G, alpha=-self.meta_lr)
 
-    def _meta_learn_collective(self) -> None:
-        """Same learned-mixer steps on the collective (NCCL/gloo) plane: deltas come from an all_gather, w is broadcast."""
-        t, ex = self.trainer, self.ex
-        g = ex.allgather_deltas(t)
+    def _meta_learn_collective(self, g: torch.Tensor) -> None:
+        """Same learned-mixer steps on the collective (NCCL/gloo) plane: ``g`` = this round's all-gathered deltas, w is
+        broadcast afterwards."""
+        t = self.trainer
         if self.rank == self.averager_rank:
             deltas = [g[i] for i in range(g.shape[0])]
             for k in range(self.meta_steps):
@@ -123,10 +123,11 @@ class LocalSGDCoordinator:
             with self.timer.phase("gather_avg"):
                 new_base = self.ex.average_broadcast(t.base)
         elif isinstance(self.ex, CollectiveExchange):
+            g = self.ex.allgather_deltas(t)  # once per round, BEFORE the mixer touches the averager's master copy
             if self.mixer == "learned" and self.meta_steps > 0 and self.val_batches:
-                self._meta_learn_collective()
+                self._meta_learn_collective(g)
             # baseline plane: NCCL/gloo all_gather + torch weighted sum (every rank computes the full average)
-            self.ex.allgather_average(t, self.w, self._new_base)
+            self.ex.allgather_average(t, self.w, self._new_base, gathered=g)
             new_base = self._new_base
         else:  # single process, no exchange object: N = 1
             t.emit_delta(self._local_delta)

@@ -99,3 +99,18 @@ def test_dummy_miner_and_wallets(tmp_path):
     led = MemoryLedger()
     ws = generate_multiple_wallets(4, str(tmp_path / "w"), ledger=led, validators=1)
     assert len(ws) == 4 and led.get("stake/test_hotkey_3") == "10000.0" and len(led.keys("hotkey/")) == 4
+
+
+def test_coordinator_collective_plane_gloo(tmp_path):
+    """Co-located round on the collective plane (gloo): all_gather of the deltas, learned-mixer steps on the averager rank,
+    weighted average on every rank.  The averager's master copy is overwritten while it evaluates candidate averages, so the
+    round must use the deltas gathered BEFORE that (regression: they used to be re-emitted afterwards)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29644", os.path.join(ROOT, "tests", "_coord_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = [json.load(open(tmp_path / f"coord_{k}.json")) for k in range(2)]
+    for x in res:
+        assert x["err_vs_manual"] < 1e-5 and x["master_is_base"] and x["moments_zero"] and x["lr"] == 5e-5, x
+        assert x["w_moved"] > 1e-6, x                       # the mixer really learned something
+    assert res[0]["base_sum"] == res[1]["base_sum"] and res[0]["w_sum"] == res[1]["w_sum"]   # identical on every rank
