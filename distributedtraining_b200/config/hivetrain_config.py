@@ -44,6 +44,7 @@ def add_b200_args(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--mixer", type=str, default="learned", choices=["learned", "uniform", "score", "genetic"])
     g.add_argument("--meta_epochs", type=int, default=7)
     g.add_argument("--meta_lr", type=float, default=0.01)
+    g.add_argument("--meta_dropout", action="store_true", help="keep dropout on in the averager's meta-gradient passes (reference behaviour; default: deterministic)")
     g.add_argument("--roles", type=str, default="", help="e.g. 'miner:0-6,validator:7,averager:0'")
     g.add_argument("--backend", type=str, default="peer", choices=["peer", "nccl", "gloo", "disk"])
     g.add_argument("--resume", action="store_true")

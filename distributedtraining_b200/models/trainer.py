@@ -20,7 +20,7 @@ class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
                  lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
-                 dropout: Optional[float] = None):
+                 dropout: Optional[float] = None, meta_dropout: bool = False):
         self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
         if dropout is not None and dropout != self.cfg.dropout:  # override the preset's train-mode dropout (0 disables)
             import dataclasses
@@ -47,6 +47,9 @@ class Trainer:
         self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
         self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk,
                                         fp8_forward=fp8_forward and self.is_cuda, seed=seed)
+        # gradients WITHOUT an optimizer step (the averager's meta-learning) are deterministic by default; True reproduces the
+        # reference, whose averager leaves dropout on
+        self.meta_dropout = bool(meta_dropout)
         self.use_graph = self.is_cuda if use_graph is None else (use_graph and self.is_cuda)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._eval_graph: Optional[torch.cuda.CUDAGraph] = None
@@ -103,17 +106,18 @@ class Trainer:
         if isinstance(input_ids, dict):
             input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
         self.engine.set_batch(input_ids, labels)
+        md = self.meta_dropout
         if not (self.use_graph and zero_grad and self.engine.n_rows == self.batch):
-            return self.engine.forward_backward(zero_grad)
+            return self.engine.forward_backward(zero_grad, dropout=md)
         if self._lg_graph is None:  # same capture protocol as step(): eager warm-up on a side stream, then capture
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self.engine.forward_backward(True)
+                self.engine.forward_backward(True, dropout=md)
             torch.cuda.current_stream().wait_stream(s)
             self._lg_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._lg_graph):
-                self.engine.forward_backward(True)
+                self.engine.forward_backward(True, dropout=md)
         self._lg_graph.replay()
         return self.engine.loss
 

@@ -502,12 +502,15 @@ class TransformerEngine:
         return self.loss
 
     # -- backward --------------------------------------------------------------------------------------------------
-    def forward_backward(self, zero_grad: bool = True) -> torch.Tensor:
+    def forward_backward(self, zero_grad: bool = True, dropout: bool = True) -> torch.Tensor:
+        """Loss + gradients of the batch in the static buffers.  ``dropout=False`` gives the deterministic (eval-mode)
+        gradient -- used by the averager's meta-learning unless ``--meta_dropout`` asks for the reference's behaviour
+        (its averager keeps the model in train mode, neurons/averager.py:69)."""
         cfg, P, G = self.cfg, self.P, self.G
         B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
         if zero_grad:
             self.grads.zero_()
-        self.forward(train=True)
+        self.forward(train=dropout)
         self._lm_head(backward=True)
         # Residual-stream gradients ping-pong between dx / dx2.  Each norm backward also produces, on the same pass, what
         # the NEXT GEMM pair in the backward order needs: its dY (a dropout-masked copy when the site is active, the

@@ -21,7 +21,8 @@ def main(argv=None):
     cfg = ctx.config
     bs = cfg.batch_size
     seq = min(EVAL_SEQ, cfg.seq_len * 8) if cfg.model.endswith("tiny") else EVAL_SEQ
-    trainer = Trainer(cfg.model, device=ctx.device, batch=bs, seq=seq, lr=cfg.lr, seed=0, use_graph=False)
+    trainer = Trainer(cfg.model, device=ctx.device, batch=bs, seq=seq, lr=cfg.lr, seed=0, use_graph=False,
+                      meta_dropout=bool(getattr(cfg, "meta_dropout", False)))
     n_batches = (EVAL_TEXTS + bs - 1) // bs if not cfg.rounds else max(1, min(4, EVAL_TEXTS // bs))
     val_loader = list(SyntheticTokens(bs, seq, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1, seed=4242,
                                       steps=n_batches, pool=n_batches))

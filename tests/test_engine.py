@@ -240,3 +240,15 @@ def test_trainer_dropout_graph_replays_fresh_masks_gpu():
     assert int(tr.engine.rng.state[1]) >= 4
     e1, e2 = float(tr.eval_loss(ids)), float(tr.eval_loss(ids))
     assert e1 == e2
+
+
+def test_meta_gradient_is_deterministic_unless_asked():
+    """Trainer.loss_and_grad (the averager's meta-gradient) ignores dropout by default and honours ``meta_dropout=True``."""
+    cfg = _with_dropout("gpt2-tiny")
+    ids = torch.randint(0, 512, (2, 16), dtype=torch.int32)
+    tr = Trainer(cfg, device="cpu", batch=2, seq=16, lr=1e-2)
+    l1 = float(tr.loss_and_grad(ids)); g1 = tr.grad.clone()
+    l2 = float(tr.loss_and_grad(ids))
+    assert l1 == l2 and torch.equal(g1, tr.grad) and abs(l1 - float(tr.eval_loss(ids))) < 1e-6
+    tr2 = Trainer(cfg, device="cpu", batch=2, seq=16, lr=1e-2, meta_dropout=True)
+    assert float(tr2.loss_and_grad(ids)) != float(tr2.loss_and_grad(ids))
