@@ -299,3 +299,31 @@ def test_checkpoint_resume(tmp_path):
     assert tr2.opt.host_step == 3 and tr2.opt.host["lr"] == pytest.approx(1e-2)
     a, b = float(tr.step(ids)), float(tr2.step(ids))
     assert abs(a - b) < 1e-6
+
+
+def test_delta_wire_formats_preserve_validator_ranking():
+    """bf16 and block-scaled fp8 deltas (the wire formats of the peer plane) must not change how a validator ranks miners:
+    score_i = max(0, loss_base - loss(theta_base + delta_i)) computed from fp32, bf16 and fp8 deltas orders the miners alike
+    (SURVEY.md 7.4.6)."""
+    from distributedtraining_b200 import ops
+    torch.manual_seed(0)
+    val = torch.randint(0, 512, (4, 16), dtype=torch.int32)
+    base_tr = Trainer("gpt2-tiny", batch=4, seq=16, lr=1e-2, seed=3)
+    base = base_tr.base.clone()
+    loss_base = float(base_tr.eval_loss(val))
+    scores = {"fp32": [], "bf16": [], "fp8": []}
+    for steps in (1, 4, 12):                                  # three miners that trained for different amounts on the val batch
+        m = Trainer("gpt2-tiny", batch=4, seq=16, lr=1e-2, seed=3)
+        for _ in range(steps):
+            m.step(val)
+        n = m.master.numel()
+        d32 = torch.empty(n); m.emit_delta(d32)
+        d16 = torch.empty(n, dtype=torch.bfloat16); m.emit_delta(d16)
+        q8, sc = torch.empty(n, dtype=torch.uint8), torch.empty(n // 32); m.emit_delta(q8, sc)
+        for name, d in (("fp32", d32), ("bf16", d16.float()), ("fp8", ops.dequant_fp8(q8, sc))):
+            base_tr.master.copy_(base + d)
+            scores[name].append(max(0.0, loss_base - float(base_tr.eval_loss(val))))
+    order = lambda xs: sorted(range(len(xs)), key=lambda i: xs[i])
+    assert order(scores["fp32"]) == order(scores["bf16"]) == order(scores["fp8"]) == [0, 1, 2], scores
+    for a, b in zip(scores["fp32"], scores["fp8"]):
+        assert abs(a - b) < 0.05 * max(a, 1e-3) + 1e-3, scores
