@@ -114,3 +114,16 @@ def test_coordinator_collective_plane_gloo(tmp_path):
         assert x["err_vs_manual"] < 1e-5 and x["master_is_base"] and x["moments_zero"] and x["lr"] == 5e-5, x
         assert x["w_moved"] > 1e-6, x                       # the mixer really learned something
     assert res[0]["base_sum"] == res[1]["base_sum"] and res[0]["w_sum"] == res[1]["w_sum"]   # identical on every rank
+
+
+def test_two_miners_one_validator_gloo_disk(tmp_path):
+    """Validator role end to end on the disk plane: both miners' deltas are scored against the base, a rank that never
+    published (the validator itself) gets score 0 like a failed download upstream."""
+    args = ["--roles", "miner:0-1,validator:2", "--device", "cpu", "--backend", "disk", "--model", "gpt2-tiny", "--batch_size", "4",
+            "--seq_len", "16", "--local_steps", "5", "--rounds", "1", "--storage.model_dir", str(tmp_path / "model"),
+            "--storage.gradient_dir", str(tmp_path / "grad"), "--metrics_jsonl", str(tmp_path / "metrics.jsonl")]
+    r = _torchrun(3, 29645, args)
+    assert r.returncode == 0, r.stderr[-3000:]
+    recs = [json.loads(l) for l in open(tmp_path / "metrics.jsonl")]
+    val = {x["hotkey"]: x for x in recs if x.get("role") == "validator" and "hotkey" in x}
+    assert val["rank0"]["loss_score"] > 0 and val["rank1"]["loss_score"] > 0 and val["rank2"]["loss_score"] == 0.0, val
