@@ -110,8 +110,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
         acc = acc + aux.float()
     elif epi == "dgelu":
         acc = acc * dgelu_tanh(aux.float())
-    elif epi == "dsilu_mul":
-        raise NotImplementedError
+    elif epi != "none" and epi not in ("bias", "bias_gelu"):
+        raise ValueError(f"unknown epilogue {epi!r}")
     if accumulate:
         out.add_(acc.to(out.dtype))
     else:
