@@ -392,3 +392,38 @@ def test_gemm_colsum_fold():
     cs2 = torch.zeros(N, device=DEV)
     ops.gemm(a, w, out, b_mn=True, colsum_out=cs2)   # plain epilogue, no aux
     _close(cs2, out.float().sum(0), rtol=1e-4)
+
+
+@pytest.mark.parametrize("epi", ["none", "bias", "bias_gelu", "bias_resid", "resid", "dgelu", "bias_resid_dropout", "f32_accumulate"])
+def test_gemm_two_sm_pairs_with_odd_tile_count(epi):
+    """Shapes large enough for the 2-SM UMMA path (tiles >= 32) with an ODD number of M-tiles (33): the second CTA of the last
+    pair owns an out-of-range tile (TMA zero-fills its operands and clips its stores).  Every epilogue, the dropout epilogue
+    and the fp32 split-K accumulate path."""
+    torch.manual_seed(21)
+    M, N, K = 33 * 128 - 5, 768, 320
+    A, B = _bf(M, K, scale=0.5), _bf(N, K, scale=0.5)
+    bias, aux = _bf(N), _bf(M, N)
+    if epi == "f32_accumulate":      # wgrad form: out[K1, K2] += X^T Y over the M tokens
+        X, Y = _bf(M, 4352, scale=0.3), _bf(M, 512, scale=0.3)     # 34 x 2 = 68 tiles of the [4352, 512] output
+        out = torch.ones(4352, 512, device=DEV)
+        ops.gemm(X, Y, out, a_mn=True, b_mn=True, accumulate=True)
+        _close(out, 1.0 + X.float().t() @ Y.float(), rtol=1e-2)
+        return
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    r = torch.empty(M, N, device=DEV)
+    if epi == "bias_resid_dropout":
+        rng = ops.DropoutRng(DEV, seed=5)
+        rng.advance()
+        dr = ops.Drop(rng, 9, 0.1)
+        ops.gemm(A, B, out, epi="bias_resid", bias=bias, aux=aux, drop=dr)
+        ref.gemm(A, B, r, epi="bias_resid", bias=bias, aux=aux, drop=dr)
+        _close(out, r, rtol=1e-2)
+        dropped = ref.drop_mult_2d(rng.state, 9, 0.1, M, N, DEV) == 0
+        assert torch.equal(out[dropped], aux[dropped])
+        return
+    out2, r2 = torch.empty_like(out), torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2 if epi == "bias_gelu" else None)
+    ref.gemm(A, B, r, epi=epi, bias=bias, aux=aux, out2=r2)
+    _close(out, r, rtol=1e-2)
+    if epi == "bias_gelu":
+        _close(out2, r2, rtol=1e-2)
