@@ -93,3 +93,15 @@ def test_parse_roles_covers_requested_ranks(world):
     if world >= 3:
         r = parse_roles(f"miner:0-{world - 3},validator:{world - 2},averager:{world - 1}", world)
         assert r["validator"] == [world - 2] and r["averager"] == [world - 1] and len(r["miner"]) == world - 2
+
+
+def test_dropout_hash_golden_values():
+    """Pins the counter-based mask arithmetic (shared bit for bit with csrc/dropout.cuh; the GPU tests compare the kernels
+    against THIS implementation, this test keeps the implementation itself from drifting)."""
+    assert ref.drop_key((7, 1), 3) == 3313189177 and ref.drop_key((0x5EED, 5), 0) == 3387426996 and ref.drop_thr(0.1) == 6554
+    m = ref.drop_mult_2d((7, 1), 3, 0.1, 8, 16, "cpu")
+    assert (m == 0).nonzero().tolist() == [[0, 2], [0, 7], [0, 8], [1, 10], [1, 14], [2, 5], [2, 6], [2, 15], [3, 5], [3, 10],
+                                            [4, 1], [4, 3], [6, 4], [6, 14], [6, 15], [7, 2], [7, 9], [7, 11]]
+    a = ref.drop_mult_attn((7, 1), 4, 0.1, 1, 8, 2, "cpu")
+    assert (a == 0).nonzero().tolist() == [[0, 0, 0, 3], [0, 0, 2, 2], [0, 0, 2, 3], [0, 0, 3, 2], [0, 0, 4, 0], [0, 0, 6, 6],
+                                            [0, 1, 0, 3], [0, 1, 2, 4], [0, 1, 2, 5], [0, 1, 4, 7], [0, 1, 5, 3], [0, 1, 7, 6]]
