@@ -104,7 +104,11 @@ class Averager:
         os.makedirs(self.local_dir, exist_ok=True)
         path = os.path.join(self.local_dir, "averaged_model.pt")
         tmp = f"{path}.tmp.{os.getpid()}"
-        torch.save(self.model.man.views(self.model.master.detach().cpu()), tmp)
+        # the reference's checkpoint format: ``model.state_dict()`` of the HF model (:481-488) -- Conv1D weights [in, out],
+        # tied lm_head present -- so ``averaged_model.pt`` loads into GPT2LMHeadModel and into every loader of this package
+        m = self.model
+        sd = m.hf_state_dict("master") if hasattr(m, "hf_state_dict") else m.man.views(m.master.detach().cpu())
+        torch.save(sd, tmp)
         os.replace(tmp, path)
         return path
 
@@ -267,7 +271,10 @@ class ParameterizedAverager(DeltaAverager):
         m = self.model
         self.get_averaged_model()
         ids, labels = _batch_ids_labels(batch)
-        loss = m.loss_and_grad(batch if not isinstance(batch, dict) else ids, labels) if hasattr(m, "loss_and_grad") else None
+        if isinstance(batch, dict) and hasattr(m, "engine"):
+            loss = m.loss_and_grad(batch)  # labels + attention_mask travel with the dict (reference :502-506)
+        else:
+            loss = m.loss_and_grad(batch if not isinstance(batch, dict) else ids, labels)
         N, P = self.weights.shape
         if self._G is None or tuple(self._G.shape) != (N, P):
             self._G = torch.empty(N, P, dtype=torch.float32, device=m.master.device)
@@ -341,8 +348,9 @@ class LocalParameterizedAverager(ParameterizedAverager):
             p = os.path.join(repo_id, gradient_file_name)
             if os.path.exists(p):
                 blob = torch.load(p, map_location="cpu", weights_only=False)
-                flat = blob if isinstance(blob, torch.Tensor) else self.model.man.pack(
-                    blob, torch.zeros(self.model.man.total, dtype=torch.float32))
+                flat = self.model.flat_from(blob) if hasattr(self.model, "flat_from") else (
+                    blob if isinstance(blob, torch.Tensor) else self.model.man.pack(
+                        blob, torch.zeros(self.model.man.total, dtype=torch.float32)))
                 return None if self.have_nans(flat) else flat
         return super().receive_gradients(repo_id, gradient_file_name)
 
@@ -385,7 +393,8 @@ class GeneticAverager(ParameterizedAverager):
             for batch in val_loader:
                 ids, labels = _batch_ids_labels(batch)
                 bs = ids.shape[0] if hasattr(ids, "shape") else len(batch[0])
-                tot += float(self.model.eval_loss(batch if not isinstance(batch, dict) else ids, labels)) * bs
+                full = isinstance(batch, dict) and hasattr(self.model, "engine")
+                tot += float(self.model.eval_loss(batch) if full else self.model.eval_loss(batch if not isinstance(batch, dict) else ids, labels)) * bs
                 n += bs
             fit.append(-tot / max(n, 1))
         return torch.tensor(fit)

@@ -44,6 +44,8 @@ struct AttnParams {
   float* lse;            // [B, H, T]
   int M, T, H, Hkv, ld_out, ld_o;
   float scale;
+  const int* kv_len;     // optional [B]: keys >= seq_start + kv_len[b] are masked for EVERY query row of sequence b (HF attention_mask
+                         // of a right-padded batch: reference hivetrain/training_manager.py:380-384); nullptr = causal only
   float* dbias;          // backward, single-block kernel only: += column sums of dqkv (the qkv bias gradient), fp32 [qkv_dim]
   DropArgs drop;  // attention-probability dropout (GPT-2 attn_pdrop): P is masked AFTER the softmax normaliser is formed
 };
@@ -60,6 +62,17 @@ DTB_DEVICE void drop_p32(float* s, uint32_t rowkey, int kg0, uint32_t thr, float
 }
 DTB_DEVICE uint32_t attn_row_key(const AttnParams& p, int h, int row_tok) {
   return p.drop.thr ? drop_row_key(drop_key(p.drop.rng, p.drop.stream), uint32_t(h) * uint32_t(p.M) + uint32_t(row_tok)) : 0u;
+}
+
+// last valid key token (absolute index) of query row `row_tok`: causal AND inside the un-padded prefix of its sequence
+DTB_DEVICE int row_last_key(const AttnParams& p, int row_tok) {
+  if (row_tok >= p.M) return -1;
+  int hi = row_tok;
+  if (p.kv_len) {
+    const int b = row_tok / p.T;
+    hi = min(hi, b * p.T + max(p.kv_len[b], 1) - 1);
+  }
+  return hi;
 }
 
 DTB_DEVICE uint32_t pack2(float a, float b) {
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     mbar_wait(bar_s, it & 1);
     tc_fence_after();
     // ---- softmax over this thread's row: pass 1 = masked row max, pass 2 = exp / sum / write P ----
-    const int c_lo = seq_start - k0, c_hi = row_tok - k0;  // valid columns: c_lo <= c <= c_hi
+    const int c_lo = seq_start - k0, c_hi = row_last_key(p, row_tok) - k0;  // valid columns: c_lo <= c <= c_hi
     float mx = -CUDART_INF_F;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
@@ -439,7 +452,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kv_kernel(const __grid_consta
     float Drow, lse_l2;
     load_row_stats(p, row_tok, hq, Drow, lse_l2);
     const int seq_start = (row_tok / p.T) * p.T;
-    const int c_lo = seq_start - k0, c_hi = (row_tok < p.M) ? row_tok - k0 : -1;
+    const int c_lo = seq_start - k0, c_hi = row_last_key(p, row_tok) - k0;
     mbar_wait(bar_s, it & 1);
     tc_fence_after();
     bwd_softmax_tiles<true>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, sP, sDS, attn_row_key(p, hq, row_tok), k0,
@@ -583,7 +596,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
       for (int k = 0; k < 4; ++k) umma_f16(tDP, ddo + uint64_t(k * 2), dv + uint64_t(k * 2), idesc_s, k > 0);
       umma_commit(bar_s);
     }
-    const int c_lo = seq_start - k0, c_hi = (row_tok < p.M) ? row_tok - k0 : -1;
+    const int c_lo = seq_start - k0, c_hi = row_last_key(p, row_tok) - k0;
     mbar_wait(bar_s, it & 1);
     tc_fence_after();
     bwd_softmax_tiles<false>(tS, tDP, lane_off, tid, c_lo, c_hi, sl2, lse_l2, Drow, p.scale, nullptr, sDS, rowkey, k0, p.drop.thr,
@@ -685,7 +698,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
       umma_commit(&bars[1]);
     }
   }
-  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_tok - q0;
+  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_last_key(p, row_tok) - q0;
   // 32-column chunks this WARP has to look at: with T % 32 == 0 all 32 rows of a warp sit in one sequence, so the chunks left
   // of the sequence start and right of the warp's last row are masked for every lane (T = 64: 1.5 of 4 chunks on average).
   int ch_lo = 0, ch_hi = 3;
@@ -856,7 +869,7 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   }
   float Drow, lse_l2;
   load_row_stats(p, row_tok, h, Drow, lse_l2);
-  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = (row_tok < p.M) ? row_tok - q0 : -1;
+  const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_last_key(p, row_tok) - q0;
   mbar_wait(&bars[1], 0);
   tc_fence_after();
   const bool uni = (p.T % 32 == 0);  // chunk window of this warp, as in the forward kernel
@@ -952,9 +965,11 @@ static void set_drop(AttnParams& p, const void* rng, int stream, float prob) {
 }
 
 extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int Hkv, int hd, int ld_qkv,
-                                 int ld_out, float scale, cudaStream_t s, const void* rng, int drop_stream, float drop_p) {
+                                 int ld_out, float scale, cudaStream_t s, const void* rng, int drop_stream, float drop_p,
+                                 const int* kv_len) {
   if (hd != kHd || H % Hkv != 0) return 10;
   AttnParams p{};
+  p.kv_len = kv_len;
   set_drop(p, rng, drop_stream, drop_p);
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
@@ -977,10 +992,11 @@ extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
 
 extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, int B, int T,
                                  int H, int Hkv, int hd, int ld_qkv, int ld_o, float scale, cudaStream_t s, const void* rng,
-                                 int drop_stream, float drop_p, float* dbias) {
+                                 int drop_stream, float drop_p, float* dbias, const int* kv_len) {
   if (hd != kHd || H % Hkv != 0) return 10;
   AttnParams p{};
   p.dbias = dbias;
+  p.kv_len = kv_len;
   set_drop(p, rng, drop_stream, drop_p);
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;

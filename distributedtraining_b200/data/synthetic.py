@@ -37,13 +37,15 @@ class SyntheticTokens:
             if pad_id < vocab:
                 ids = torch.where(mask, ids, torch.full_like(ids, pad_id))  # right padding, like tokenizer(padding="max_length")
             ids = ids.to(torch.int32)
-            b = {"input_ids": ids, "attention_mask": mask.to(torch.int32), "labels": ids.clone()}
+            # "kv_len" = attention_mask.sum(-1): the padding mask in the form the attention kernels consume (4 B per row)
+            b = {"input_ids": ids, "attention_mask": mask.to(torch.int32), "labels": ids.clone(),
+                 "kv_len": lens.to(torch.int32) if pad_id < vocab else torch.full((batch,), seq, dtype=torch.int32)}
             if device != "cpu":
                 b = {k: v.to(device) for k, v in b.items()}
             elif pin:
                 b = {k: v.pin_memory() for k, v in b.items()}
             self.pool.append(b)
-        self.bytes_per_batch = batch * seq * 4  # input_ids only: labels/mask are derived on the device
+        self.bytes_per_batch = batch * seq * 4 + batch * 4  # input_ids + kv_len: labels / mask are derived on the device
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         i = 0

@@ -19,6 +19,7 @@ from typing import Dict, Optional, Union
 import torch
 
 from .models.arena import Manifest
+from .models.transformer import pack_any
 from .parallel.exchange import DiskExchange, Exchange
 from .utils.logging import logger
 
@@ -43,18 +44,20 @@ def parse_repo(repo_id: Union[str, int, None]) -> Optional[int]:
 class HFManager:
     def __init__(self, local_dir: str = ".", hf_token: Optional[str] = None, my_repo_id=None, averaged_model_repo_id=None,
                  model_dir: Optional[str] = None, device: str = "cuda", exchange: Optional[Exchange] = None,
-                 manifest: Optional[Manifest] = None):
+                 manifest: Optional[Manifest] = None, model_config=None):
         self.my_repo_id = my_repo_id
         self.model_repo_id = averaged_model_repo_id
         self.hf_token = hf_token  # accepted for signature compatibility; never used
         self.device = device
         self.exchange = exchange
         self.manifest = manifest if manifest is not None else getattr(exchange, "man", None)
+        self.model_config = model_config  # ModelConfig: lets file-based pushes accept HF-layout (reference-format) dicts
         self.local_dir = local_dir
         self.local_gradient_dir = os.path.join(local_dir, str(my_repo_id).split("/")[-1]) if my_repo_id is not None else None
         self.model_dir = model_dir if model_dir else os.path.join(local_dir, str(averaged_model_repo_id).split("/")[-1])
         self.round = 0  # number of deltas published by this manager
         self._staged_base: Optional[torch.Tensor] = None
+        self._published_round = 0  # last base round this manager published (averager side)
         # record the current version so that the first check is False until the averager publishes again
         # (reference hf_manager.py:54)
         self.latest_model_commit_sha = self.get_latest_commit_sha(self.model_repo_id)
@@ -83,7 +86,7 @@ class HFManager:
             if trainer is None:
                 path = os.path.join(self.get_local_gradient_directory(), file_to_send)
                 sd = torch.load(path, map_location="cpu", weights_only=False)
-                trainer = _DictDelta(self.manifest, sd)
+                trainer = _DictDelta(self.manifest, sd, self.model_config)
             self.exchange.publish_delta(trainer, self.round)
         except Exception as e:  # best-effort, as in the reference (hf_manager.py:113-114)
             logger.warning(f"Failed to push changes: {e}")
@@ -118,10 +121,12 @@ class HFManager:
         try:
             if base is None:
                 blob = torch.load(path_to_model, map_location="cpu", weights_only=False)
-                base = blob if isinstance(blob, torch.Tensor) else self.manifest.pack(
-                    blob, torch.zeros(self.manifest.total, dtype=torch.float32))
-            nxt = (self.exchange.base_round() + 1) if round is None else round
+                base = pack_any(self.manifest, blob, self.model_config)
+            # the published round is tracked HERE as well: a peer-plane publisher only sees its own slot after the flag
+            # kernel has run, and re-deriving "next" from a stale read would republish the same round forever
+            nxt = (max(int(self.exchange.base_round()), self._published_round) + 1) if round is None else int(round)
             self.exchange.publish_base(base, nxt)
+            self._published_round = nxt
             self.latest_model_commit_sha = str(nxt)
         except Exception as e:
             logger.warning(f"Failed to push model: {e}")
@@ -175,8 +180,8 @@ class HFManager:
 class _DictDelta:
     """Adapter: a ``dict[name, Tensor]`` delta presented with the ``emit_delta`` interface of a trainer."""
 
-    def __init__(self, manifest: Manifest, sd: Dict[str, torch.Tensor]):
-        self.flat = manifest.pack(sd, torch.zeros(manifest.total, dtype=torch.float32))
+    def __init__(self, manifest: Manifest, sd: Dict[str, torch.Tensor], cfg=None):
+        self.flat = pack_any(manifest, sd, cfg)
         self.master = self.flat
 
     def emit_delta(self, out, scales=None):
@@ -188,12 +193,13 @@ class LocalHFManager(HFManager):
     """Shared-directory hub (reference hf_manager.py:200-241): "new submission" == sha256 of ``averaged_model.pt`` changed."""
 
     def __init__(self, my_repo_id=".", averaged_model_repo_id=".", device: str = "cpu", manifest: Optional[Manifest] = None,
-                 rank: int = 0, delta_dtype: str = "fp32"):
+                 rank: int = 0, delta_dtype: str = "fp32", model_config=None):
         self.root = str(averaged_model_repo_id)
         exchange = DiskExchange(self.root, rank, manifest, delta_dtype)
         self.last_known_hash: Optional[str] = None
         super().__init__(local_dir=str(my_repo_id), my_repo_id=rank, averaged_model_repo_id=averaged_model_repo_id,
-                         model_dir=os.path.join(self.root, "base"), device=device, exchange=exchange, manifest=manifest)
+                         model_dir=os.path.join(self.root, "base"), device=device, exchange=exchange, manifest=manifest,
+                         model_config=model_config)
         self.local_gradient_dir = str(my_repo_id)
         self.last_known_hash = exchange.base_hash()
 

@@ -95,8 +95,14 @@ class Manifest:
         return {s.name: flat[s.offset:s.offset + s.numel].view(s.shape) for s in self.specs}
 
     def pack(self, tensors: Dict[str, torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+        """Flatten a name->tensor dict into ``out``.  Shapes must match the manifest exactly (the reference's shape
+        screen, averaging_logic.py:406-410): a transposed / foreign-layout tensor of the right numel is an error, never a
+        silent scramble -- convert HF-layout dicts with ``models.transformer.from_hf_state_dict`` first."""
         for s in self.specs:
-            out[s.offset:s.offset + s.numel].copy_(tensors[s.name].reshape(-1))
+            t = tensors[s.name]
+            if tuple(t.shape) != s.shape:
+                raise ValueError(f"{s.name}: shape {tuple(t.shape)} does not match the manifest's {s.shape}")
+            out[s.offset:s.offset + s.numel].copy_(t.reshape(-1))
         return out
 
     # -- segment tables for the segmented kernels ------------------------------------------------------------------

@@ -7,20 +7,26 @@ sync (the loss stays on the device), no per-tensor Python loops, launch overhead
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 
 from .. import ops
 from .arena import Manifest
-from .transformer import ModelConfig, TransformerEngine, build_manifest, get_config, new_model
+from .transformer import (ModelConfig, TransformerEngine, build_manifest, from_hf_state_dict, get_config, load_hf_checkpoint,
+                          new_model, pack_any, to_hf_state_dict)
 
 
 class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
                  lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
-                 dropout: Optional[float] = None, meta_dropout: bool = False):
+                 dropout: Optional[float] = None, meta_dropout: bool = False, dropout_seed: Optional[int] = None):
+        if isinstance(model, str) and os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):
+            # an HF checkpoint directory, as the reference's ``AutoModelForCausalLM.from_pretrained(model_name)`` + [PAD]
+            # resize (hivetrain/training_manager.py:39-46)
+            model, _, init_flat = load_hf_checkpoint(model, add_pad_token=True)
         self.cfg: ModelConfig = get_config(model) if isinstance(model, str) else model
         if dropout is not None and dropout != self.cfg.dropout:  # override the preset's train-mode dropout (0 disables)
             import dataclasses
@@ -46,7 +52,10 @@ class Trainer:
             self.p16 = self.master  # CPU: compute directly on the fp32 master
         self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
         self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk,
-                                        fp8_forward=fp8_forward and self.is_cuda, seed=seed)
+                                        fp8_forward=fp8_forward and self.is_cuda,
+                                        seed=seed if dropout_seed is None else dropout_seed)
+        # ``seed`` fixes the (shared) initial weights; ``dropout_seed`` decorrelates the dropout masks of co-located miners
+        # (every rank is built with seed=0 so that all share theta_base -- their masks must still differ: pass the rank)
         # gradients WITHOUT an optimizer step (the averager's meta-learning) are deterministic by default; True reproduces the
         # reference, whose averager leaves dropout on
         self.meta_dropout = bool(meta_dropout)
@@ -67,9 +76,10 @@ class Trainer:
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimizer step on a [B,T] batch (host-pinned or device).  Returns the device-resident mean loss."""
-        if isinstance(input_ids, dict):
-            input_ids, labels = input_ids["input_ids"], None  # miner: labels = input_ids (PAD not masked)
-        self.engine.set_batch(input_ids, labels)
+        if isinstance(input_ids, dict):  # miner: labels = input_ids (PAD not masked), attention_mask -> padding-masked attention
+            self.engine.set_batch(input_ids["input_ids"], None, input_ids.get("attention_mask"), input_ids.get("kv_len"))
+        else:
+            self.engine.set_batch(input_ids, labels)
         assert self.engine.n_rows == self.batch, "training batches must fill the static batch"
         if not self.use_graph:
             c0 = ops.launch_count()
@@ -103,9 +113,7 @@ class Trainer:
     def loss_and_grad(self, input_ids, labels: Optional[torch.Tensor] = None, zero_grad: bool = True) -> torch.Tensor:
         """Forward + backward at the CURRENT master/p16 without an optimizer step: grads land in ``self.grad``.
         (The averager's meta-learning needs dL/dtheta_bar: reference hivetrain/averaging_logic.py:502-511.)"""
-        if isinstance(input_ids, dict):
-            input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
-        self.engine.set_batch(input_ids, labels)
+        self.engine.set_batch(input_ids, labels)  # dict batches carry labels / attention_mask themselves
         md = self.meta_dropout
         if not (self.use_graph and zero_grad and self.engine.n_rows == self.batch):
             return self.engine.forward_backward(zero_grad, dropout=md)
@@ -123,8 +131,6 @@ class Trainer:
 
     @torch.no_grad()
     def eval_loss(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if isinstance(input_ids, dict):
-            input_ids, labels = input_ids["input_ids"], input_ids.get("labels", labels)
         self.engine.set_batch(input_ids, labels)
         return self.engine.forward_loss()
 
@@ -143,6 +149,26 @@ class Trainer:
             self.opt.reset()
         if lr is not None:
             self.opt.set_lr(lr)
+
+    # -- HF interoperability -------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, path_or_state_dict, model=None, add_pad_token: bool = True, **kw) -> "Trainer":
+        """Start from pretrained weights like the reference miner / validator / averager do (training_manager.py:39-46,
+        neurons/validator.py:52-58): an HF checkpoint directory, or an HF-layout ``state_dict`` plus the ``model`` preset
+        it belongs to.  The embedding table is grown by the ``[PAD]`` row when the checkpoint is one row short."""
+        if isinstance(path_or_state_dict, str):
+            cfg, _, flat = load_hf_checkpoint(path_or_state_dict, add_pad_token=add_pad_token)
+            return cls(cfg, init_flat=flat, **kw)
+        cfg = get_config(model) if isinstance(model, str) else model
+        return cls(cfg, init_flat=from_hf_state_dict(cfg, path_or_state_dict), **kw)
+
+    def hf_state_dict(self, which: str = "master") -> Dict[str, torch.Tensor]:
+        """HF / reference-format state dict of ``master`` or ``base`` (loads into ``GPT2LMHeadModel`` as is)."""
+        return to_hf_state_dict(self.cfg, getattr(self, which).detach().float().cpu())
+
+    def flat_from(self, blob) -> torch.Tensor:
+        """Flat fp32 arena from a flat tensor / engine-layout dict / HF-layout dict (shape-screened)."""
+        return pack_any(self.man, blob, self.cfg)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {"master": self.master, "base": self.base, "m": self.m, "v": self.v, "step": self.opt.step,

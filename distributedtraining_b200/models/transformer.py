@@ -72,7 +72,16 @@ PRESETS: Dict[str, ModelConfig] = {
 }
 
 
-def get_config(name: str) -> ModelConfig:
+def get_config(name) -> ModelConfig:
+    if isinstance(name, ModelConfig):
+        return name
+    import os
+    if os.path.isdir(name) and os.path.exists(os.path.join(name, "config.json")):  # HF checkpoint directory (+ [PAD] row)
+        import dataclasses
+        import json
+        with open(os.path.join(name, "config.json")) as f:
+            c = config_from_hf(json.load(f))
+        return dataclasses.replace(c, vocab_size=c.vocab_size + 1)
     key = name.lower().replace("openai-community/", "").replace("_", "-")
     if key not in PRESETS:
         raise KeyError(f"unknown model {name!r}; known: {sorted(PRESETS)}")
@@ -208,10 +217,19 @@ def drop_stream(site: str, l: int = 0) -> int:
     return {"embd": 0, "attn": 1 + 3 * l, "resid1": 2 + 3 * l, "resid2": 3 + 3 * l}[site]
 
 
+def kv_len_of(attention_mask: Optional[torch.Tensor], T: int) -> Optional[torch.Tensor]:
+    """int32 [B] count of un-padded keys per sequence from an HF ``attention_mask`` of a RIGHT-padded batch (the
+    reference's tokenizer pads right: neurons/miner.py:78-92); clamped to >= 1 (an all-PAD row keeps its first key)."""
+    if attention_mask is None:
+        return None
+    return attention_mask.reshape(-1, T).sum(dim=1).clamp_(min=1).to(torch.int32)
+
+
 def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_ids: torch.Tensor,
-                  drop_state=None) -> torch.Tensor:
+                  drop_state=None, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Plain autograd forward.  ``drop_state`` (the engine's ``rng.state`` AFTER its advance, or a (seed, counter) tuple)
-    turns on train-mode dropout with exactly the masks the kernels generate."""
+    turns on train-mode dropout with exactly the masks the kernels generate.  ``attention_mask`` [B,T]: padding mask as
+    the reference passes it to HF GPT-2 (keys of PAD positions are invisible to every query)."""
     from ..ops import reference as ref
     P = ModelParams(cfg, man, theta)
     B, T = input_ids.shape
@@ -223,7 +241,7 @@ def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_id
         x = x + P.wpe[:T][None]
     if pd > 0:
         x = x * dm("embd")
-    mask = torch.ones(T, T, dtype=torch.bool, device=theta.device).tril()
+    mask = ref.attn_mask(B, T, theta.device, kv_len_of(attention_mask, T))
     for l, L in enumerate(P.layers):
         h = _norm(cfg, x, L.ln1_w, L.ln1_b)
         qkv = F.linear(h, L.qkv_w, L.qkv_b)
@@ -256,8 +274,8 @@ def oracle_logits(cfg: ModelConfig, man: Manifest, theta: torch.Tensor, input_id
     return F.linear(x, P.wte)
 
 
-def oracle_loss(cfg, man, theta, input_ids, labels=None, drop_state=None) -> torch.Tensor:
-    logits = oracle_logits(cfg, man, theta, input_ids, drop_state)
+def oracle_loss(cfg, man, theta, input_ids, labels=None, drop_state=None, attention_mask=None) -> torch.Tensor:
+    logits = oracle_logits(cfg, man, theta, input_ids, drop_state, attention_mask)
     tgt = make_targets(input_ids, labels)
     return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), tgt.view(-1).long(), ignore_index=-1)
 
@@ -341,7 +359,12 @@ class TransformerEngine:
             self.a8 = torch.empty(M * max(Fd, d, cfg.n_head * cfg.head_dim), dtype=torch.uint8, device=self.dev)
         self.targets = torch.full((batch, seq), -1, dtype=torch.int32, device=self.dev)
         self.ids = torch.zeros((batch, seq), dtype=torch.int32, device=self.dev)
+        # un-padded keys per sequence (HF attention_mask of a right-padded batch); = T when no mask is given.  Always passed
+        # to the attention kernels so that a captured CUDA graph serves masked and unmasked batches alike.
+        self.kvlen = torch.full((batch,), seq, dtype=torch.int32, device=self.dev)
         self.n_rows = batch
+        self._kv_masked = False
+        self.loss_denominator: Optional[int] = None  # override of the CE normaliser (data-parallel meta-learning)
 
     # -- helpers ---------------------------------------------------------------------------------------------------
     def _norm_fwd(self, x, w, b, out, mean, rstd):
@@ -359,9 +382,19 @@ class TransformerEngine:
     def _drop(self, site: str, l: int = 0):
         return ops.Drop(self.rng, drop_stream(site, l), self.drop_p) if self._dropping else None
 
-    def set_batch(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> None:
+    def set_batch(self, input_ids, labels: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                  kv_len: Optional[torch.Tensor] = None) -> None:
         """Copy a batch into the static id/target buffers (non-blocking when the source is pinned).  A batch with fewer
-        than B rows (last eval batch) is padded with ignored rows; the loss is normalised by the real row count."""
+        than B rows (last eval batch) is padded with ignored rows; the loss is normalised by the real row count.
+        ``input_ids`` may be the reference's batch dict {"input_ids", "attention_mask", "labels"[, "kv_len"]}.
+        ``attention_mask`` [B,T] (or the pre-reduced ``kv_len`` [B]) masks PAD keys exactly like HF GPT-2 does for the
+        reference (training_manager.py:380-384); without it attention is causal-only."""
+        if isinstance(input_ids, dict):
+            d = input_ids
+            input_ids = d["input_ids"]
+            labels = d.get("labels", labels) if labels is None else labels
+            attention_mask = d.get("attention_mask", attention_mask)
+            kv_len = d.get("kv_len", kv_len)
         ids2 = input_ids.view(-1, self.T)
         n = ids2.shape[0]
         assert n <= self.B, f"batch of {n} rows exceeds the engine's static batch {self.B}"
@@ -372,6 +405,15 @@ class TransformerEngine:
             self.targets[n:].fill_(-1)
         self.ids[:n].copy_(ids2, non_blocking=True)
         self.targets[:n, :-1].copy_(src[:, 1:], non_blocking=True)
+        if kv_len is None and attention_mask is not None:
+            kv_len = kv_len_of(attention_mask, self.T)
+        if kv_len is not None:
+            self.kvlen[:n].copy_(kv_len.view(-1)[:n], non_blocking=True)
+            if n < self.B:
+                self.kvlen[n:].fill_(self.T)
+        elif self._kv_masked:
+            self.kvlen.fill_(self.T)
+        self._kv_masked = kv_len is not None
 
     # -- forward ---------------------------------------------------------------------------------------------------
     def set_delta(self, delta_flat: Optional[torch.Tensor]) -> None:
@@ -448,7 +490,8 @@ class TransformerEngine:
             self._fgemm(l, "qkv_w", self.h1[l], self.qkv[l], epi="bias" if Lp.qkv_b is not None else "none", bias=Lp.qkv_b)
             if cfg.family == "llama":
                 ops.rope_(self.qkv[l], B, T, H, Hkv, hd, cfg.rope_theta)
-            ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv, drop=self._drop("attn", l))
+            ops.attention_fwd(self.qkv[l], self.att[l], self.lse[l], B, T, H, hd, Hkv, drop=self._drop("attn", l),
+                              kv_len=self.kvlen)
             self._fgemm(l, "o_w", self.att[l], self.xmid[l], epi="bias_resid" if Lp.o_b is not None else "resid", bias=Lp.o_b,
                         aux=x, drop=self._drop("resid1", l))
             self._norm_fwd(self.xmid[l], Lp.ln2_w, Lp.ln2_b, self.h2[l], self.mean2[l], self.rstd2[l])
@@ -464,7 +507,7 @@ class TransformerEngine:
     def _lm_head(self, backward: bool) -> None:
         cfg, P = self.cfg, self.P
         V = cfg.vocab_size
-        n_valid = self.n_rows * (self.T - 1)
+        n_valid = self.loss_denominator if self.loss_denominator is not None else self.n_rows * (self.T - 1)
         scale = 1.0 / max(n_valid, 1)
         tgt = self.targets.view(-1)
         first = True
@@ -546,7 +589,7 @@ class TransformerEngine:
             ops.gemm(dy, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
             # d(qkv bias) = colsum(dqkv) rides on the attention backward (GPT-2 has no RoPE between the two)
             ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv,
-                              drop=self._drop("attn", l), dbias=Lg.qkv_b)
+                              drop=self._drop("attn", l), dbias=Lg.qkv_b, kv_len=self.kvlen)
             if cfg.family == "llama":
                 ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
             ops.gemm(self.dqkv, Lp.qkv_w, self.dh, b_mn=True)
@@ -561,17 +604,118 @@ class TransformerEngine:
         return self.loss
 
 
-def to_hf_state_dict(cfg: ModelConfig, arena: Arena) -> Dict[str, torch.Tensor]:
-    """HF-compatible state dict (GPT-2 Conv1D weights transposed back to [in, out]; tied lm_head added -> 149 keys)."""
+_CONV1D = ("c_attn.weight", "c_proj.weight", "c_fc.weight")  # HF GPT-2 stores these [in, out]; the engine [out, in]
+
+
+def to_hf_state_dict(cfg: ModelConfig, arena) -> Dict[str, torch.Tensor]:
+    """HF-compatible state dict (GPT-2 Conv1D weights transposed back to [in, out]; tied lm_head added -> 149 keys):
+    loads straight into ``transformers.GPT2LMHeadModel`` / ``LlamaForCausalLM`` -- the reference's checkpoint format
+    (``model.state_dict()``, hivetrain/averaging_logic.py:481-488).  ``arena``: an :class:`Arena` or a flat tensor."""
+    if isinstance(arena, torch.Tensor):
+        arena = Arena(build_manifest(cfg), flat=arena)
     sd = arena.state_dict(clone=True)
     if cfg.family == "gpt2":
         for k in list(sd):
-            if k.endswith(("c_attn.weight", "c_proj.weight", "c_fc.weight")):
+            if k.endswith(_CONV1D):
                 sd[k] = sd[k].t().contiguous()
         sd["lm_head.weight"] = sd["transformer.wte.weight"]
     else:
         sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
     return sd
+
+
+def is_hf_layout(cfg: ModelConfig, sd: Dict[str, torch.Tensor]) -> bool:
+    """HF GPT-2 layout is recognisable by the (non-square) c_attn weight being [d, 3d]; Llama layouts coincide."""
+    if cfg.family != "gpt2":
+        return True
+    w = sd.get("transformer.h.0.attn.c_attn.weight")
+    return w is not None and tuple(w.shape) == (cfg.n_embd, 3 * cfg.n_embd)
+
+
+def from_hf_state_dict(cfg: ModelConfig, sd: Dict[str, torch.Tensor], man: Optional[Manifest] = None,
+                       out: Optional[torch.Tensor] = None, resize_vocab: bool = True) -> torch.Tensor:
+    """HF state dict (``GPT2LMHeadModel`` / ``LlamaForCausalLM`` naming, or this engine's own layout) -> flat fp32 arena.
+
+    * GPT-2 Conv1D weights are transposed to the engine's ``[out, in]`` (the square ``attn.c_proj`` cannot be told apart
+      by shape -- the layout is detected on ``c_attn`` and applied to all of them);
+    * ``lm_head.weight`` (tied) and the non-parameter buffers (``attn.bias`` / ``masked_bias``) are dropped;
+    * ``resize_vocab``: a checkpoint with FEWER embedding rows than ``cfg.vocab_size`` is grown the way the reference does
+      after adding ``[PAD]`` (``resize_token_embeddings``, hivetrain/training_manager.py:39-46): the new rows are set to
+      the mean of the existing embeddings (HF's ``mean_resizing`` without the sampled covariance term, so that every rank
+      derives the SAME base without communication);
+    * every other shape mismatch raises (the reference's shape screen, averaging_logic.py:406-410).
+    """
+    man = man or build_manifest(cfg)
+    out = out if out is not None else torch.zeros(man.total, dtype=torch.float32)
+    hf = is_hf_layout(cfg, sd)
+    emb = "transformer.wte.weight" if cfg.family == "gpt2" else "model.embed_tokens.weight"
+    for spec in man.specs:
+        if spec.name not in sd:
+            raise KeyError(f"checkpoint lacks {spec.name}")
+        t = sd[spec.name].detach().to(torch.float32)
+        if hf and cfg.family == "gpt2" and spec.name.endswith(_CONV1D):
+            t = t.t()
+        if spec.name == emb and resize_vocab and t.shape[0] < spec.shape[0] and t.shape[1:] == spec.shape[1:]:
+            grown = t.mean(dim=0, keepdim=True).expand(spec.shape[0], -1).clone()
+            grown[:t.shape[0]] = t
+            t = grown
+        if tuple(t.shape) != spec.shape:
+            raise ValueError(f"{spec.name}: checkpoint shape {tuple(sd[spec.name].shape)} does not fit {spec.shape}")
+        out[spec.offset:spec.offset + spec.numel].copy_(t.reshape(-1))
+    return out
+
+
+def pack_any(man: Manifest, blob, cfg: Optional[ModelConfig] = None) -> torch.Tensor:
+    """Flat fp32 arena from whatever a peer handed over: a flat tensor, an engine-layout dict, or (with ``cfg``) an HF /
+    reference-format state dict (``averaged_model.pt``, ``weight_diff.pt``, ``gradients.pt``).  Wrong shapes raise."""
+    if isinstance(blob, torch.Tensor):
+        if blob.numel() != man.total:
+            raise ValueError(f"flat tensor of {blob.numel()} elements does not fit the manifest ({man.total})")
+        return blob
+    if cfg is not None:
+        return from_hf_state_dict(cfg, blob, man, resize_vocab=False)
+    return man.pack(blob, torch.zeros(man.total, dtype=torch.float32))
+
+
+def config_from_hf(d: dict) -> ModelConfig:
+    """``config.json`` of an HF GPT-2 / Llama checkpoint -> ModelConfig."""
+    mt = d.get("model_type", "gpt2")
+    if mt == "gpt2":
+        return ModelConfig(family="gpt2", name=d.get("_name_or_path") or "gpt2-hf", vocab_size=int(d["vocab_size"]),
+                           n_positions=int(d.get("n_positions", 1024)), n_embd=int(d["n_embd"]), n_layer=int(d["n_layer"]),
+                           n_head=int(d["n_head"]), ffn=d.get("n_inner") or None, eps=float(d.get("layer_norm_epsilon", 1e-5)),
+                           dropout=float(d.get("resid_pdrop", 0.1)))
+    if mt == "llama":
+        return ModelConfig(family="llama", name=d.get("_name_or_path") or "llama-hf", vocab_size=int(d["vocab_size"]),
+                           n_positions=int(d.get("max_position_embeddings", 8192)), n_embd=int(d["hidden_size"]),
+                           n_layer=int(d["num_hidden_layers"]), n_head=int(d["num_attention_heads"]),
+                           n_kv_head=int(d.get("num_key_value_heads", d["num_attention_heads"])),
+                           ffn=int(d["intermediate_size"]), eps=float(d.get("rms_norm_eps", 1e-5)),
+                           rope_theta=float(d.get("rope_theta", 10000.0)))
+    raise ValueError(f"unsupported HF model_type {mt!r}")
+
+
+def load_hf_checkpoint(path: str, add_pad_token: bool = True) -> Tuple[ModelConfig, Manifest, torch.Tensor]:
+    """Read an HF checkpoint DIRECTORY (``config.json`` + ``model.safetensors`` | ``pytorch_model.bin``) without
+    instantiating a ``transformers`` model.  ``add_pad_token`` grows the vocabulary by one row, as every reference role
+    does (``tokenizer.add_special_tokens({'pad_token': '[PAD]'})`` + ``resize_token_embeddings``, neurons/miner.py:60-62)."""
+    import json
+    import os
+    with open(os.path.join(path, "config.json")) as f:
+        cfg = config_from_hf(json.load(f))
+    st = os.path.join(path, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        sd = load_file(st)
+    else:
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    if cfg.family == "gpt2" and not any(k.startswith("transformer.") for k in sd):
+        sd = {"transformer." + k: v for k, v in sd.items()}  # bare GPT2Model checkpoints
+    if add_pad_token:
+        import dataclasses
+        cfg = dataclasses.replace(cfg, vocab_size=cfg.vocab_size + 1)
+    man = build_manifest(cfg)
+    return cfg, man, from_hf_state_dict(cfg, sd, man)
 
 
 def new_model(name_or_cfg, device="cpu", dtype=torch.float32, seed: int = 0) -> Tuple[ModelConfig, Manifest, Arena]:

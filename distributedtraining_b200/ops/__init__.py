@@ -308,14 +308,14 @@ def colsum(x, out):
 # ---------------------------------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None, kv_len=None):
     from . import attention as _att
-    return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop)
+    return _att.attention_fwd(qkv, out, lse, B, T, H, hd, Hkv, drop, kv_len)
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None, dbias=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None, dbias=None, kv_len=None):
     from . import attention as _att
-    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop, dbias)
+    return _att.attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv, drop, dbias, kv_len)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

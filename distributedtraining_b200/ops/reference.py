@@ -205,7 +205,17 @@ def _split_qkv(qkv, B, T, H, Hkv, hd):
     return q, k, v
 
 
-def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
+def attn_mask(B, T, device, kv_len=None):
+    """[B,1,T,T] bool: key c is visible to query r iff c <= r (causal) and c < kv_len[b] (padding mask of a right-padded
+    batch, HF ``attention_mask`` semantics: reference hivetrain/training_manager.py:380-384); kv_len is clamped to >= 1."""
+    mask = torch.ones(T, T, dtype=torch.bool, device=device).tril()[None, None]
+    if kv_len is not None:
+        key_ok = torch.arange(T, device=device)[None, :] < kv_len.to(device).long().clamp(min=1)[:, None]
+        mask = mask & key_ok[:, None, None, :]
+    return mask.expand(B, 1, T, T)
+
+
+def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None, kv_len=None):
     """Causal self-attention over packed qkv [B*T, (H+2Hkv)*hd] -> out [B*T, H*hd]; lse [B,H,T] fp32 (natural log).
     ``drop``: dropout on the softmax probabilities (the normaliser / lse are those of the un-dropped softmax)."""
     Hkv = Hkv or H
@@ -214,7 +224,7 @@ def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
         k = k.repeat_interleave(H // Hkv, dim=1)
         v = v.repeat_interleave(H // Hkv, dim=1)
     s = (q.float() @ k.float().transpose(-1, -2)) / math.sqrt(hd)
-    mask = torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
+    mask = attn_mask(B, T, qkv.device, kv_len)
     s = s.masked_fill(~mask, float("-inf"))
     l = torch.logsumexp(s, dim=-1)
     p = torch.exp(s - l[..., None])
@@ -227,7 +237,7 @@ def attention_fwd(qkv, out, lse, B, T, H, hd, Hkv=None, drop=None):
     return out
 
 
-def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
+def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None, kv_len=None):
     Hkv = Hkv or H
     rep = H // Hkv
     q, k, v = _split_qkv(qkv, B, T, H, Hkv, hd)
@@ -238,7 +248,7 @@ def attention_bwd(dout, qkv, out, lse, dqkv, B, T, H, hd, Hkv=None, drop=None):
     o = out.view(B, T, H, hd).transpose(1, 2).float()
     scale = 1.0 / math.sqrt(hd)
     s = (q @ kx.transpose(-1, -2)) * scale
-    mask = torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
+    mask = attn_mask(B, T, qkv.device, kv_len)
     p = torch.exp(s - lse[..., None]).masked_fill(~mask, 0.0)
     dp = do @ vx.transpose(-1, -2)
     if drop is not None and drop.p > 0:

@@ -216,6 +216,7 @@ class PeerExchange(Exchange):
         self.nan_flags = torch.zeros(max(self.world, 1), dtype=torch.int32, device=self.win.device)
         self._base_round = 0
         self.with_base16 = with_base16
+        self._snap = {}  # src rank -> local snapshot buffer of its delta (fetch_delta)
 
     # -- miner side -------------------------------------------------------------------------------------------------
     def delta_buf(self, round: int, rank: Optional[int] = None) -> torch.Tensor:
@@ -243,16 +244,37 @@ class PeerExchange(Exchange):
         stale = set(self.win.stale_ranks(min_beat))
         return [r for r in (range(self.world) if miners is None else miners) if r in stale]
 
-    def fetch_delta(self, src: int, round: int) -> Optional[torch.Tensor]:
-        latest = int(self.win.flags()[self.F_DELTA + src].item())
-        if latest < max(round, 1):
-            return None  # stale flag / never published == failed download in the reference
-        if round <= 0:
-            round = latest  # "whatever the miner published last" (the reference downloads the repo head)
-        d = self.delta_buf(round, src)[:self.man.total]
-        if self.delta_dtype_name == "fp8":
-            return ops.dequant_fp8(d, self.scale_buf(round, src))
-        return d
+    def fetch_delta(self, src: int, round: int, snapshot: bool = True) -> Optional[torch.Tensor]:
+        """Delta of miner ``src`` (``round <= 0``: whatever it published last), ``None`` if nothing (new enough) is there.
+
+        The window is a 2-deep round-parity ring that an asynchronous miner keeps overwriting, so by default the delta is
+        SNAPSHOT into local HBM with one device copy and validated seqlock-style: the publish flag is re-read after the
+        copy and the snapshot only counts if no newer round was published meanwhile (the buffer of round r is next written
+        for round r+2, whose emit starts only after round r+1 was flagged) -- otherwise retry on the newer round.  The
+        reference's download is atomic in the same sense (hf_manager.py:186-197).  ``snapshot=False`` returns the
+        zero-copy peer view (synchronous rounds, where the producer cannot run ahead)."""
+        n = self.man.total
+        for _ in range(4):
+            latest = int(self.win.flags()[self.F_DELTA + src].item())
+            if latest < max(round, 1):
+                return None  # stale flag / never published == failed download in the reference
+            r = latest if round <= 0 else max(round, latest)  # always the newest complete publication
+            d = self.delta_buf(r, src)[:n]
+            sc = self.scale_buf(r, src)
+            if not snapshot:
+                return ops.dequant_fp8(d, sc) if self.delta_dtype_name == "fp8" else d
+            if self.delta_dtype_name == "fp8":
+                snap = ops.dequant_fp8(d, sc)  # materialises a local fp32 copy
+            else:
+                snap = self._snap.get(src)
+                if snap is None or snap.numel() != n:
+                    snap = self._snap[src] = torch.empty(n, dtype=self.delta_dtype, device=self.win.device)
+                snap.copy_(d)
+            after = int(self.win.flags()[self.F_DELTA + src].item())  # .item() orders the read after the copy
+            if after == r:
+                return snap
+            round = after  # a newer round landed while we copied: the buffer may be torn, take the newer one
+        return None
 
     # -- averager side ------------------------------------------------------------------------------------------------
     def _delta_ptrs(self, round: int, miners: Sequence[int]) -> Tuple[List[int], Optional[List[int]]]:
@@ -331,8 +353,14 @@ class PeerExchange(Exchange):
         self._base_round = round
         self.win.publish(self.F_BASE, round, dst)
 
-    def base_round(self, src: int = 0) -> int:
-        return int(self.win.flags()[self.F_BASE + src].item())
+    def base_round(self, src: Optional[int] = None) -> int:
+        """Newest base round visible in this rank's flag page.  ``SymmetricWindow.publish`` writes slot
+        ``F_BASE + <publisher rank>``, and the averager may sit on ANY rank (``--roles miner:0-6,averager:7``), so the
+        default is the maximum over all publisher slots; ``src`` reads one publisher's slot."""
+        f = self.win.flags()
+        if src is not None:
+            return int(f[self.F_BASE + src].item())
+        return int(f[self.F_BASE:self.F_BASE + max(self.world, 1)].max().item())
 
     def base_view(self) -> torch.Tensor:
         return self.win.local("base", torch.float32)[:self.man.total]

@@ -45,7 +45,8 @@ def build_context(role: str, argv=None, config: Optional[Config] = None) -> Cont
         backend = "disk"
     rank, world, device = init_distributed("gloo" if cfg.device == "cpu" else "nccl", cfg)
     roles = parse_roles(cfg.roles, world)
-    man = build_manifest(get_config(cfg.model))
+    model_cfg = get_config(cfg.model)
+    man = build_manifest(model_cfg)
     hotkey = f"rank{rank}"
     cfg.wallet.hotkey = hotkey
     # ---- ledger: the job's store when distributed, a JSON file for independent local processes, memory otherwise ----
@@ -72,7 +73,7 @@ def build_context(role: str, argv=None, config: Optional[Config] = None) -> Cont
     my_repo = cfg.storage.my_repo_id or f"{scheme}://{rank}"
     hf = HFManager(local_dir=cfg.storage.gradient_dir, my_repo_id=my_repo if role == "miner" else None,
                    averaged_model_repo_id=cfg.storage.averaged_model_repo_id, model_dir=cfg.storage.model_dir,
-                   device=str(device), exchange=exchange, manifest=man)
+                   device=str(device), exchange=exchange, manifest=man, model_config=model_cfg)
     chain = ChainMultiAddressStore(BittensorNetwork.ledger, cfg.netuid, BittensorNetwork.wallet)
     if role == "miner":  # register my endpoint once (the reference commits its HF repo id to the chain)
         if chain.retrieve_hf_repo(hotkey) != my_repo:

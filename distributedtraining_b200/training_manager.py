@@ -71,6 +71,8 @@ class TrainingLoop:
         self.model_name = model_name
         # the reference loads tokenizer + AutoModelForCausalLM.from_pretrained here (:39-46); offline we build the
         # named architecture with random init (or take an injected trainer, like TrainingLoopNew does)
+        # ``model_name`` may also be an HF checkpoint DIRECTORY: it is then loaded and grown by the [PAD] row exactly like
+        # the reference constructor does (from_pretrained + add [PAD] + resize_token_embeddings, :39-46)
         self.model = trainer if trainer is not None else Trainer(model_name, device=device, batch=batch_size, seq=seq_len,
                                                                  lr=learning_rate, seed=seed)
         self.hf_manager = hf_manager
@@ -84,6 +86,7 @@ class TrainingLoop:
         self.max_steps = max_steps
         self.metrics = metrics or MetricsLogger(None, "miner")
         self.round_hook = round_hook
+        self.checkpoint_hook = None  # callable(loop) run after every completed round (periodic --save_every)
         self.last_pull_time = 0.0
         self.last_send_time = time.time()
         self.global_step = 0
@@ -220,6 +223,8 @@ class DeltaLoop(TrainingLoop):
             self.rounds_sent += 1
             self._log_round(epoch)
             self.last_send_time = time.time()
+            if getattr(self, "checkpoint_hook", None) is not None:
+                self.checkpoint_hook(self)
         except Exception as e:  # best effort, as in the reference (:428-431)
             logger.warning(f"Sending gradients failed: {e}")
             self.last_send_time = time.time()

@@ -64,7 +64,9 @@ class ModelValidator:
         self._sync_compute_copy()
 
     def _as_flat(self, t) -> torch.Tensor:
-        if isinstance(t, dict):
+        if isinstance(t, dict):  # name->tensor dict in the engine's or in the reference's (HF) layout
+            if hasattr(self.model, "flat_from"):
+                return self.model.flat_from(t)
             return self.model.man.pack(t, torch.zeros(self.model.man.total, dtype=torch.float32))
         return t
 
@@ -86,7 +88,9 @@ class ModelValidator:
         for batch in self.data_loader or []:
             ids, labels = _batch_ids_labels(batch)
             bs = ids.shape[0] if hasattr(ids, "shape") else len(ids[0])
-            loss = self.model.eval_loss(ids, labels)
+            # dict batches go through whole: the engine applies their attention_mask as the padding mask (reference :85-90)
+            loss = self.model.eval_loss(batch) if isinstance(batch, dict) and hasattr(self.model, "engine") else \
+                self.model.eval_loss(ids, labels)
             acc = loss.detach().double() * bs if acc is None else acc + loss.detach().double() * bs  # stays on device
             n += bs
         if acc is None:

@@ -22,8 +22,8 @@ def main(argv=None):
     cfg = ctx.config
     batch_size = cfg.batch_size
     trainer = Trainer(cfg.model, device=ctx.device, batch=batch_size, seq=cfg.seq_len, lr=cfg.lr, seed=0,
-                      dropout=getattr(cfg, "dropout", None))
-    maybe_resume(cfg, trainer, ctx.rank)
+                      dropout=getattr(cfg, "dropout", None), dropout_seed=ctx.rank)
+    resumed_round = maybe_resume(cfg, trainer, ctx.rank)
     # reference: WikiText-103 train split @ max_length 64, no shuffle (neurons/miner.py:54-106); offline: synthetic tokens
     data_loader = SyntheticTokens(batch_size, cfg.seq_len, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1,
                                   seed=ctx.rank)
@@ -32,9 +32,19 @@ def main(argv=None):
                      hf_manager=ctx.hf_manager, trainer=trainer, local_steps=None if cfg.wall_clock else cfg.local_steps,
                      post_pull_lr=cfg.post_pull_lr, reset_optimizer=not cfg.no_reset_optimizer, max_steps=max_steps,
                      metrics=ctx.metrics, my_hotkey=ctx.hotkey)
+    if resumed_round:  # continue the round numbering: a fresh_only averager ignores rounds it has already consumed
+        loop.rounds_sent = resumed_round
+        loop.global_step = resumed_round * (cfg.local_steps or 0)
+        if ctx.hf_manager is not None:
+            ctx.hf_manager.round = resumed_round
+        if max_steps is not None:
+            loop.max_steps = max_steps + loop.global_step
+    if cfg.save_every:  # periodic: every ``save_every`` rounds (the reference parses the flag and never reads it)
+        loop.checkpoint_hook = lambda lp: (lp.rounds_sent % cfg.save_every == 0) and save_checkpoint(
+            cfg, trainer, ctx.rank, lp.rounds_sent, extra={"global_step": lp.global_step})
     loop.train(epochs=int(3e16) if max_steps is None else 1)
     if cfg.save_every:
-        save_checkpoint(cfg, trainer, ctx.rank, loop.rounds_sent)
+        save_checkpoint(cfg, trainer, ctx.rank, loop.rounds_sent, extra={"global_step": loop.global_step})
     return loop
 
 
