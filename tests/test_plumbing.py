@@ -29,7 +29,7 @@ def test_two_miners_one_averager_gloo_disk(tmp_path):
         assert int(open(tmp_path / "model" / "deltas" / f"weight_diff_{rk}.pt.round").read()) == 2
     assert int(open(tmp_path / "model" / "base" / "averaged_model.pt.round").read()) >= 1
     sd = torch.load(tmp_path / "model" / "averaged_model.pt", weights_only=False)
-    assert len(sd) == 28 and all(torch.isfinite(v).all() for v in sd.values())
+    assert len(sd) == 29 and "lm_head.weight" in sd and all(torch.isfinite(v).all() for v in sd.values())
     recs = [json.loads(l) for l in open(tmp_path / "metrics.jsonl")]
     assert any(r.get("role") == "averager" and "loss_averaged" in r for r in recs)
     assert any(r.get("role") == "miner" and "train_loss" in r for r in recs)
