@@ -17,13 +17,9 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
-#include "sm100_ptx.cuh"
+#include "avg_common.cuh"
 
 namespace dtb {
-
-using bf16 = __nv_bfloat16;
-constexpr int kMaxMiners = 64;
-constexpr int kMaxOut = 16;
 
 // ------------------------------------------------------------------------------------------------------------------
 // AdamW
@@ -89,13 +85,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, 
 // mode 0: fp32, 1: bf16, 2: fp8 e4m3 with one fp32 scale per 32 elements (scale = amax/448; q = x/scale)
 __global__ void __launch_bounds__(256) delta_emit_kernel(const float* __restrict__ master, const float* __restrict__ base,
                                                          void* __restrict__ out, float* __restrict__ scales, size_t n,
-                                                         int mode) {
+                                                         int mode, int* __restrict__ bad) {
   // each thread handles 8 consecutive elements; 4 threads cooperate on one 32-element fp8 block
   const size_t n8 = n / 8;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
     const float4 a0 = reinterpret_cast<const float4*>(master)[2 * i], a1 = reinterpret_cast<const float4*>(master)[2 * i + 1];
     const float4 b0 = reinterpret_cast<const float4*>(base)[2 * i], b1 = reinterpret_cast<const float4*>(base)[2 * i + 1];
     float d[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w, a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+    if (bad) {  // NaN/Inf screen at the SOURCE (reference averaging_logic.py:121-127 screens after the download): the verdict
+                // travels with the publish flag, so every consumer agrees on it without re-reading the delta
+      float z = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z += d[k] * 0.f;
+      if (z != 0.f) *bad = 1;
+    }
     if (mode == 0) {
       reinterpret_cast<float4*>(out)[2 * i] = make_float4(d[0], d[1], d[2], d[3]);
       reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(d[4], d[5], d[6], d[7]);
@@ -179,6 +182,7 @@ struct AvgParams {
   int unit_base;                       // 1: theta = base + sum_i w_i delta_i (delta APPLY), 0: s_j = sum_i w_ij (averaging)
   int ld_mode;                         // peer-load flavour, see ld_peer_v4
   uint32_t wait_value;
+  const int* active;                   // optional [N] device mask (round_prepare_kernel): inactive miners are neither read nor weighted
 };
 
 // Peer-load flavour (set once per process through DTB200_PEER_LD = sys | nc | weak; default sys):
@@ -230,20 +234,22 @@ __device__ __forceinline__ void load_delta8(const AvgParams& p, int i, size_t e,
 template <int MODE>
 __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__ AvgParams p) {
   __shared__ float s_w[kMaxMiners + 1];
+  __shared__ int s_idx[kMaxMiners];  // compacted list of the miners that take part (active mask)
+  __shared__ int s_n;
   // --- wait for the producers' publish flags (fused "barrier-by-flag" instead of the reference's SHA polling) ---
   if (p.wait_value != 0) {
-    if (threadIdx.x < p.N && p.wait_flag[threadIdx.x] != nullptr) {
-      long long spins = 0;
-      while (ld_acquire_sys(p.wait_flag[threadIdx.x]) < p.wait_value) {
-        if (++spins > (1ll << 26)) {
-          *p.error_flag = 1;
-          break;
-        }
-        __nanosleep(200);
-      }
-    }
+    if (threadIdx.x < p.N && p.wait_flag[threadIdx.x] != nullptr && !(p.active && !p.active[threadIdx.x]))
+      wait_flag_ge(p.wait_flag[threadIdx.x], p.wait_value, p.error_flag);
     __syncthreads();
   }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < p.N; ++i)
+      if (!p.active || p.active[i]) s_idx[n++] = i;
+    s_n = n;
+  }
+  __syncthreads();
+  const int NA = s_n;
   int bad = 0;  // bitmask (per thread) of miners with non-finite data; N <= 64 -> two 32-bit words
   int bad_hi = 0;
   for (int ci = p.chunk_begin + blockIdx.x; ci < p.chunk_end; ci += gridDim.x) {
@@ -252,11 +258,11 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
     const size_t start = size_t(p.chunk_start[c]);
     const int len = p.chunk_len[c];
     __syncthreads();
-    if (threadIdx.x < p.N) s_w[threadIdx.x] = p.w[size_t(threadIdx.x) * p.P + j];
+    if (threadIdx.x < NA) s_w[threadIdx.x] = p.w[size_t(s_idx[threadIdx.x]) * p.P + j];
     __syncthreads();
     if (threadIdx.x == 0) {
       float s = 0.f;
-      for (int i = 0; i < p.N; ++i) s += s_w[i];
+      for (int i = 0; i < NA; ++i) s += s_w[i];
       s_w[kMaxMiners] = p.unit_base ? 1.f : s;
     }
     __syncthreads();
@@ -267,12 +273,13 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
       const float4 b1 = reinterpret_cast<const float4*>(p.base + e)[1];
       float acc[8] = {b0.x * s_sum, b0.y * s_sum, b0.z * s_sum, b0.w * s_sum, b1.x * s_sum, b1.y * s_sum, b1.z * s_sum, b1.w * s_sum};
       int i = 0;
-      for (; i + 4 <= p.N; i += 4) {  // 4 miners' loads in flight per thread before the FMAs
+      for (; i + 4 <= NA; i += 4) {  // 4 miners' loads in flight per thread before the FMAs
+        const int m0 = s_idx[i], m1 = s_idx[i + 1], m2 = s_idx[i + 2], m3 = s_idx[i + 3];
         float d0[8], d1[8], d2[8], d3[8];
-        load_delta8<MODE>(p, i, e, d0);
-        load_delta8<MODE>(p, i + 1, e, d1);
-        load_delta8<MODE>(p, i + 2, e, d2);
-        load_delta8<MODE>(p, i + 3, e, d3);
+        load_delta8<MODE>(p, m0, e, d0);
+        load_delta8<MODE>(p, m1, e, d1);
+        load_delta8<MODE>(p, m2, e, d2);
+        load_delta8<MODE>(p, m3, e, d3);
         const float w0 = s_w[i], w1 = s_w[i + 1], w2 = s_w[i + 2], w3 = s_w[i + 3];
         float chk0 = 0.f, chk1 = 0.f, chk2 = 0.f, chk3 = 0.f;
 #pragma unroll
@@ -280,14 +287,15 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
           acc[k] += w0 * d0[k] + w1 * d1[k] + w2 * d2[k] + w3 * d3[k];
           chk0 += d0[k] * 0.f; chk1 += d1[k] * 0.f; chk2 += d2[k] * 0.f; chk3 += d3[k] * 0.f;  // NaN/Inf -> NaN
         }
-        if (chk0 != 0.f) { if (i < 32) bad |= 1 << i; else bad_hi |= 1 << (i - 32); }
-        if (chk1 != 0.f) { if (i + 1 < 32) bad |= 1 << (i + 1); else bad_hi |= 1 << (i + 1 - 32); }
-        if (chk2 != 0.f) { if (i + 2 < 32) bad |= 1 << (i + 2); else bad_hi |= 1 << (i + 2 - 32); }
-        if (chk3 != 0.f) { if (i + 3 < 32) bad |= 1 << (i + 3); else bad_hi |= 1 << (i + 3 - 32); }
+        if (chk0 != 0.f) { if (m0 < 32) bad |= 1 << m0; else bad_hi |= 1 << (m0 - 32); }
+        if (chk1 != 0.f) { if (m1 < 32) bad |= 1 << m1; else bad_hi |= 1 << (m1 - 32); }
+        if (chk2 != 0.f) { if (m2 < 32) bad |= 1 << m2; else bad_hi |= 1 << (m2 - 32); }
+        if (chk3 != 0.f) { if (m3 < 32) bad |= 1 << m3; else bad_hi |= 1 << (m3 - 32); }
       }
-      for (; i < p.N; ++i) {
+      for (; i < NA; ++i) {
+        const int m0 = s_idx[i];
         float d0[8];
-        load_delta8<MODE>(p, i, e, d0);
+        load_delta8<MODE>(p, m0, e, d0);
         const float w0 = s_w[i];
         float chk0 = 0.f;
 #pragma unroll
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
           acc[k] += w0 * d0[k];
           chk0 += d0[k] * 0.f;
         }
-        if (chk0 != 0.f) { if (i < 32) bad |= 1 << i; else bad_hi |= 1 << (i - 32); }
+        if (chk0 != 0.f) { if (m0 < 32) bad |= 1 << m0; else bad_hi |= 1 << (m0 - 32); }
       }
       const float4 o0 = make_float4(acc[0], acc[1], acc[2], acc[3]), o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
       uint4 ob;
@@ -342,16 +350,8 @@ struct ShardPullParams {
 
 __global__ void __launch_bounds__(256) shard_pull_reset_kernel(const __grid_constant__ ShardPullParams p) {
   if (p.wait_value != 0) {
-    if (threadIdx.x < p.world && p.wait_flag[threadIdx.x] != nullptr) {
-      long long spins = 0;
-      while (ld_acquire_sys(p.wait_flag[threadIdx.x]) < p.wait_value) {
-        if (++spins > (1ll << 26)) {
-          *p.error_flag = 1;
-          break;
-        }
-        __nanosleep(200);
-      }
-    }
+    if (threadIdx.x < p.world && p.wait_flag[threadIdx.x] != nullptr)
+      wait_flag_ge(p.wait_flag[threadIdx.x], p.wait_value, p.error_flag);
     __syncthreads();
   }
   for (int c = blockIdx.x; c < p.num_chunks; c += gridDim.x) {
@@ -376,124 +376,6 @@ __global__ void __launch_bounds__(256) shard_pull_reset_kernel(const __grid_cons
         *reinterpret_cast<float4*>(p.v + e) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// segmented multi-dot (meta-gradient).  Stage 1: per chunk partial sums [num_chunks, N+1]; stage 2: per tensor reduce.
-// ------------------------------------------------------------------------------------------------------------------
-struct DotParams {
-  const void* delta[kMaxMiners];
-  const float* dscale[kMaxMiners];
-  const float* g;
-  const float* base;
-  const float* avg;
-  const int64_t* chunk_start;
-  const int32_t* chunk_len;
-  float* partial;  // [num_chunks, N+1]
-  int N, num_chunks, mode;
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(256) multi_dot_stage1(const __grid_constant__ DotParams p) {
-  __shared__ float red[8][kMaxMiners + 1];
-  AvgParams* dummy = nullptr;
-  (void)dummy;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  for (int c = blockIdx.x; c < p.num_chunks; c += gridDim.x) {
-    const size_t start = size_t(p.chunk_start[c]);
-    const int len = p.chunk_len[c];
-    float common = 0.f;
-    float acc[kMaxMiners];
-#pragma unroll 1
-    for (int i = 0; i < p.N; ++i) acc[i] = 0.f;
-    for (int v8 = threadIdx.x; v8 * 8 < len; v8 += blockDim.x) {
-      const size_t e = start + size_t(v8) * 8;
-      float g[8], b[8], a[8];
-      *reinterpret_cast<float4*>(g) = reinterpret_cast<const float4*>(p.g + e)[0];
-      *reinterpret_cast<float4*>(g + 4) = reinterpret_cast<const float4*>(p.g + e)[1];
-      *reinterpret_cast<float4*>(b) = reinterpret_cast<const float4*>(p.base + e)[0];
-      *reinterpret_cast<float4*>(b + 4) = reinterpret_cast<const float4*>(p.base + e)[1];
-      *reinterpret_cast<float4*>(a) = reinterpret_cast<const float4*>(p.avg + e)[0];
-      *reinterpret_cast<float4*>(a + 4) = reinterpret_cast<const float4*>(p.avg + e)[1];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) common += g[k] * (b[k] - a[k]);
-#pragma unroll 1
-      for (int i = 0; i < p.N; ++i) {
-        float d[8];
-        // reuse the averaging kernel's typed loader through a layout-compatible view of the pointer tables
-        if (MODE == 0) {
-          const uint4 q0 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e);
-          const uint4 q1 = ld_relaxed_sys_v4(reinterpret_cast<const float*>(p.delta[i]) + e + 4);
-          d[0] = __uint_as_float(q0.x); d[1] = __uint_as_float(q0.y); d[2] = __uint_as_float(q0.z); d[3] = __uint_as_float(q0.w);
-          d[4] = __uint_as_float(q1.x); d[5] = __uint_as_float(q1.y); d[6] = __uint_as_float(q1.z); d[7] = __uint_as_float(q1.w);
-        } else if (MODE == 1) {
-          const uint4 q = ld_relaxed_sys_v4(reinterpret_cast<const bf16*>(p.delta[i]) + e);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 t = __bfloat1622float2(h[k]);
-            d[2 * k] = t.x;
-            d[2 * k + 1] = t.y;
-          }
-        } else {
-          uint2 q;
-          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y)
-                       : "l"(reinterpret_cast<const uint8_t*>(p.delta[i]) + e) : "memory");
-          float sc;
-          asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc) : "l"(p.dscale[i] + (e >> 5)) : "memory");
-          const uint8_t* bb = reinterpret_cast<const uint8_t*>(&q);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const __half_raw hr = __nv_cvt_fp8_to_halfraw(bb[k], __NV_E4M3);
-            d[k] = __half2float(*reinterpret_cast<const __half*>(&hr)) * sc;
-          }
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += g[k] * d[k];
-        acc[i] += s;
-      }
-    }
-    // block reduce N+1 values
-    for (int i = 0; i <= p.N; ++i) {
-      float vsum = (i == p.N) ? common : acc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-      if (lane == 0) red[wib][i] = vsum;
-    }
-    __syncthreads();
-    if (threadIdx.x <= p.N) {
-      float s = 0.f;
-      for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-      p.partial[size_t(c) * (p.N + 1) + threadIdx.x] = s;
-    }
-    __syncthreads();
-  }
-}
-
-// one block per tensor j: out[i, j] = sum_chunks partial[c, i] + sum_chunks partial[c, N]
-__global__ void __launch_bounds__(256) multi_dot_stage2(const float* __restrict__ partial, const int32_t* __restrict__ first_chunk,
-                                                        float* __restrict__ out, int N, int P) {
-  __shared__ float red[8][kMaxMiners + 1];
-  const int j = blockIdx.x;
-  const int c0 = first_chunk[j], c1 = first_chunk[j + 1];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  for (int i = 0; i <= N; ++i) {
-    float s = 0.f;
-    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) s += partial[size_t(c) * (N + 1) + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red[wib][i] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < N) {
-    float s = 0.f, cm = 0.f;
-    for (int wv = 0; wv < 8; ++wv) {
-      s += red[wv][threadIdx.x];
-      cm += red[wv][N];
-    }
-    out[size_t(threadIdx.x) * P + j] = s + cm;
   }
 }
 
@@ -527,24 +409,17 @@ struct FlagParams {
   uint32_t* dst[kMaxMiners];  // one flag word per destination rank (peer-mapped)
   int n;
   uint32_t value;
+  const int* cond;            // optional device predicate: publish ``value`` if *cond != 0, else 0
 };
 // Publish: make all prior writes of this GPU visible system-wide, then release-store the round number to every peer.
 __global__ void publish_flag_kernel(const __grid_constant__ FlagParams p) {
   __threadfence_system();
-  if (threadIdx.x < p.n && p.dst[threadIdx.x]) st_release_sys(p.dst[threadIdx.x], p.value);
+  const uint32_t v = (p.cond == nullptr || *p.cond != 0) ? p.value : 0u;
+  if (threadIdx.x < p.n && p.dst[threadIdx.x]) st_release_sys(p.dst[threadIdx.x], v);
 }
 // Wait until all of flags[0..n) >= value (local polling).
 __global__ void wait_flags_kernel(const uint32_t* flags, int n, int stride, uint32_t value, int* error_flag) {
-  if (threadIdx.x < n) {
-    long long spins = 0;
-    while (ld_acquire_sys(flags + size_t(threadIdx.x) * stride) < value) {
-      if (++spins > (1ll << 26)) {
-        *error_flag = 1;
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
+  if (threadIdx.x < n) wait_flag_ge(flags + size_t(threadIdx.x) * stride, value, error_flag);
 }
 
 }  // namespace dtb
@@ -608,8 +483,8 @@ extern "C" int dtb_adamw(float* master, void* p16, const float* grad, float* m, 
   return KCHECK();
 }
 extern "C" int dtb_delta_emit(const float* master, const float* base, void* out, float* scales, size_t n, int mode, int num_sms,
-                              cudaStream_t s) {
-  delta_emit_kernel<<<num_sms * 8, 256, 0, s>>>(master, base, out, scales, n, mode);
+                              cudaStream_t s, int* bad) {
+  delta_emit_kernel<<<num_sms * 8, 256, 0, s>>>(master, base, out, scales, n, mode, bad);
   return KCHECK();
 }
 extern "C" int dtb_cast_f32_bf16(const float* src, void* dst, size_t n, int num_sms, cudaStream_t s) {
@@ -627,9 +502,10 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
                               const float* base, const float* w, const int64_t* chunk_start, const int32_t* chunk_len,
                               const int32_t* chunk_tid, int chunk_begin, int chunk_end, float** outs_f32, void** outs_bf16,
                               int n_out, int* nan_flags, int* error_flag, int N, int P, int mode, int grid, cudaStream_t s,
-                              const int32_t* chunk_ids, int unit_base) {
+                              const int32_t* chunk_ids, int unit_base, const int* active) {
   if (N > kMaxMiners || n_out > kMaxOut) return 3;
   AvgParams p{};
+  p.active = active;
   for (int i = 0; i < N; ++i) {
     p.delta[i] = deltas[i];
     p.dscale[i] = dscales ? dscales[i] : nullptr;
@@ -659,31 +535,15 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
   return KCHECK();
 }
 
-extern "C" int dtb_multi_dot(const void** deltas, const float** dscales, const float* g, const float* base, const float* avg,
-                             const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* first_chunk, float* partial,
-                             float* out, int N, int P, int num_chunks, int mode, int grid, cudaStream_t s) {
-  if (N > kMaxMiners) return 3;
-  DotParams p{};
-  for (int i = 0; i < N; ++i) {
-    p.delta[i] = deltas[i];
-    p.dscale[i] = dscales ? dscales[i] : nullptr;
-  }
-  p.g = g; p.base = base; p.avg = avg; p.chunk_start = chunk_start; p.chunk_len = chunk_len; p.partial = partial;
-  p.N = N; p.num_chunks = num_chunks; p.mode = mode;
-  if (grid > num_chunks) grid = num_chunks;
-  if (mode == 0) multi_dot_stage1<0><<<grid, 256, 0, s>>>(p);
-  else if (mode == 1) multi_dot_stage1<1><<<grid, 256, 0, s>>>(p);
-  else multi_dot_stage1<2><<<grid, 256, 0, s>>>(p);
-  if (cudaGetLastError() != cudaSuccess) return 1;
-  multi_dot_stage2<<<P, 256, 0, s>>>(partial, first_chunk, out, N, P);
-  return KCHECK();
+extern "C" int dtb_set_flag_timeout_optim(double seconds) {
+  const long long polls = seconds <= 0 ? (1ll << 62) : (long long)(seconds / 200e-9);
+  return cudaMemcpyToSymbol(g_spin_limit, &polls, sizeof(polls)) == cudaSuccess ? 0 : 1;
 }
-
-extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStream_t s) {
+extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStream_t s, const int* cond) {
   if (n > kMaxMiners) return 3;
   FlagParams p{};
   for (int i = 0; i < n; ++i) p.dst[i] = dsts[i];
-  p.n = n; p.value = value;
+  p.n = n; p.value = value; p.cond = cond;
   publish_flag_kernel<<<1, 64, 0, s>>>(p);
   return KCHECK();
 }

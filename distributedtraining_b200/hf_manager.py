@@ -184,8 +184,10 @@ class _DictDelta:
         self.flat = pack_any(manifest, sd, cfg)
         self.master = self.flat
 
-    def emit_delta(self, out, scales=None):
+    def emit_delta(self, out, scales=None, bad=None):
         out.copy_(self.flat.to(out.device, out.dtype))
+        if bad is not None and not bool(torch.isfinite(self.flat).all()):
+            bad.fill_(1)
         return out
 
 

@@ -110,8 +110,8 @@ class ModuleTrainer:
         self.module.train(was)
         return out
 
-    def emit_delta(self, out, scales=None):
-        return ops.delta_emit(self.master, self.base, out, scales)
+    def emit_delta(self, out, scales=None, bad=None):
+        return ops.delta_emit(self.master, self.base, out, scales, bad)
 
     def load_base(self, new_base, lr: Optional[float] = None, reset_optimizer: bool = True):
         if new_base.data_ptr() != self.base.data_ptr():

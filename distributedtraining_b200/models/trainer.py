@@ -135,9 +135,10 @@ class Trainer:
         return self.engine.forward_loss()
 
     # ------------------------------------------------------------------------------------------------------------
-    def emit_delta(self, out: torch.Tensor, scales: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """delta = theta - theta_base into ``out`` (usually this rank's symmetric window)."""
-        return ops.delta_emit(self.master, self.base, out, scales)
+    def emit_delta(self, out: torch.Tensor, scales: Optional[torch.Tensor] = None, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """delta = theta - theta_base into ``out`` (usually this rank's symmetric window); ``bad`` (int32[1]) is raised when
+        the delta holds a NaN/Inf."""
+        return ops.delta_emit(self.master, self.base, out, scales, bad)
 
     def load_base(self, new_base: torch.Tensor, lr: Optional[float] = None, reset_optimizer: bool = True) -> None:
         """Adopt a new averaged base: theta = theta_base = new_base; optimizer re-created (moments dropped) with the

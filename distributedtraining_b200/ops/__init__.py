@@ -365,15 +365,19 @@ def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None)
 DELTA_MODES = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2, getattr(torch, "float8_e4m3fn", None): 2}
 
 
-def delta_emit(master, base, out, scales=None):
-    """out = master - base in out's dtype; fp8 (uint8/float8_e4m3fn storage) is block-scaled: ``scales`` fp32[n/32]."""
+def delta_emit(master, base, out, scales=None, bad=None):
+    """out = master - base in out's dtype; fp8 (uint8/float8_e4m3fn storage) is block-scaled: ``scales`` fp32[n/32].
+    ``bad`` (int32[1], optional): set to 1 when the delta holds a NaN/Inf -- the NaN screen done at the source."""
     if not use_kernels(master):
+        if bad is not None and not bool(torch.isfinite(master.float() - base.float()).all()):
+            bad.fill_(1)
         if scales is not None:
             return ref_delta_emit_fp8(master, base, out, scales)
         return ref.delta_emit(master, base, out)
     mode = DELTA_MODES[out.dtype]
     _c(_lib.lib().dtb_delta_emit(_lib.ptr(master), _lib.ptr(base), _lib.ptr(out), _lib.ptr(scales),
-                                 ctypes.c_size_t(master.numel()), mode, _lib.num_sms(), _lib.stream_ptr()), "delta_emit")
+                                 ctypes.c_size_t(master.numel()), mode, _lib.num_sms(), _lib.stream_ptr(), _lib.ptr(bad)),
+       "delta_emit")
     _tick()
     return out
 
@@ -433,11 +437,13 @@ def _dp(t) -> int:
 
 
 def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales=None, nan_flags=None, wait_flags=None,
-                 wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None, chunk_ids=None, unit_base=False):
+                 wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None, chunk_ids=None, unit_base=False,
+                 active=None):
     """Fused kernel (a): ``theta_new = s_j*base + sum_i w[i,j]*delta_i`` written to every destination in ``outs_*``.
 
     ``deltas`` / ``outs_*`` entries are tensors or raw (peer-mapped) device addresses.  ``chunk_range`` restricts the
-    launch to a shard of the manifest's chunk table (reduce-scatter form).  See csrc/optim_avg.cu.
+    launch to a shard of the manifest's chunk table (reduce-scatter form).  ``active`` (int32 [N], device): miners whose
+    entry is 0 are neither read nor weighted (NaN / missing deltas, see :func:`round_prepare`).  See csrc/optim_avg.cu.
     """
     N, P = w.shape
     if not isinstance(outs_f32, (list, tuple)):
@@ -449,6 +455,9 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
         dl = list(deltas)
         if dscales is not None:
             dl = [dequant_fp8(d, s) for d, s in zip(deltas, dscales)]
+        if active is not None:
+            keep = [i for i in range(N) if int(active[i]) != 0]
+            dl, w = [dl[i] for i in keep], w[keep]
         tmp = torch.empty_like(base, dtype=torch.float32)
         ref.weighted_avg(base, dl, w, tid, tmp, nan_flags)
         if unit_base:
@@ -482,10 +491,48 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
         _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None, ctypes.c_uint32(wait_value),
         _lib.ptr(base), _lib.ptr(w), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(ct), c0, c1, _ptr_array(of), _ptr_array(ob),
         n_out, _lib.ptr(nan_flags), _lib.ptr(error_flag), N, P, mode, grid or _lib.num_sms() * 8, _lib.stream_ptr(),
-        _lib.ptr(chunk_ids), int(unit_base))
+        _lib.ptr(chunk_ids), int(unit_base), _lib.ptr(active))
     _c(rc, "gather_avg")
     _tick()
     return outs_f32[0]
+
+
+def _first_chunk(manifest, device) -> torch.Tensor:
+    """int32 [P + 1]: index of the first chunk of every manifest tensor in the chunk table."""
+    key = ("first_chunk", str(device))
+    cache = manifest._chunk_cache
+    if key not in cache:
+        _, _, ct = manifest.seg_table(device)
+        first = torch.searchsorted(ct.long().contiguous(), torch.arange(len(manifest) + 1, device=device)).to(torch.int32)
+        cache[key] = (first, first, first)
+    return cache[key][0]
+
+
+def seg_dot(gs, deltas, base, avg, manifest, dsts, *, N, gscales=None, wait_flags=None, wait_value=0, dscales=None, mode=0,
+            chunk_range=None, active=None, loss=None, loss_scale=1.0, error_flag=None, partial=None):
+    """Meta-gradient partial over a chunk range, for all miners at once (csrc/meta_avg.cu):
+
+        dst[i*P + j] = sum_{e in tensor j, chunks [c0, c1)} gs[e] * (delta_i[e] + base[e] - avg[e]),   gs = sum_r gscales[r] * gs[r]
+
+    ``gs`` / ``deltas`` / ``dsts`` entries are tensors or raw (peer-mapped) addresses; with R > 1 gradient arenas the
+    reduce-scatter of the data-parallel validation gradients is fused into the dot.  ``dsts``: tables of N*P + 1 floats (the
+    last entry receives ``loss * loss_scale``).  Deterministic (fixed reduction order)."""
+    dev = base.device
+    cs, cl, _ = manifest.seg_table(dev)
+    P = len(manifest)
+    c0, c1 = chunk_range if chunk_range is not None else (0, cs.numel())
+    if partial is None:
+        partial = torch.empty(max(c1 - c0, 1) * (N + 1), dtype=torch.float32, device=dev)
+    R = len(gs)
+    rc = _lib.lib().dtb_seg_dot(
+        _ptr_array([_dp(g) for g in gs]), (ctypes.c_float * R)(*[float(x) for x in (gscales or [1.0] * R)]),
+        _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None, ctypes.c_uint32(wait_value), R,
+        _ptr_array([_dp(d) for d in deltas]), _ptr_array([_dp(x) for x in dscales]) if dscales is not None else None, N, mode,
+        _lib.ptr(base), _lib.ptr(avg), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(_first_chunk(manifest, dev)), c0, c1, P,
+        _lib.ptr(partial), _ptr_array([_dp(d) for d in dsts]), len(dsts), _lib.ptr(active), _lib.ptr(loss),
+        ctypes.c_float(loss_scale), _lib.ptr(error_flag), _lib.num_sms() * 4, _lib.stream_ptr())
+    _c(rc, "seg_dot")
+    _tick(2)
 
 
 def multi_dot(g, deltas, base, avg, manifest, out, *, dscales=None, mode=None):
@@ -497,24 +544,63 @@ def multi_dot(g, deltas, base, avg, manifest, out, *, dscales=None, mode=None):
         if dscales is not None:
             dl = [dequant_fp8(d, s) for d, s in zip(deltas, dscales)]
         return ref.multi_dot(g, dl, base, avg, tid, P, out)
-    cs, cl, ct = manifest.seg_table(g.device)
-    nchunks = cs.numel()
-    key = ("first_chunk", str(g.device))
-    cache = manifest._chunk_cache
-    if key not in cache:
-        first = torch.searchsorted(ct.long().contiguous(), torch.arange(P + 1, device=g.device)).to(torch.int32)
-        cache[key] = (first, first, first)
-    first = cache[key][0]
-    partial = torch.empty(nchunks * (N + 1), dtype=torch.float32, device=g.device)
     if mode is None:
         mode = 2 if dscales is not None else DELTA_MODES[deltas[0].dtype]
-    rc = _lib.lib().dtb_multi_dot(
-        _ptr_array([_dp(d) for d in deltas]), _ptr_array([_dp(s) for s in dscales]) if dscales is not None else None,
-        _lib.ptr(g), _lib.ptr(base), _lib.ptr(avg), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(first), _lib.ptr(partial),
-        _lib.ptr(out), N, P, nchunks, mode, _lib.num_sms() * 4, _lib.stream_ptr())
-    _c(rc, "multi_dot")
-    _tick(2)
+    table = torch.empty(N * P + 1, dtype=torch.float32, device=g.device)
+    seg_dot([g], deltas, base, avg, manifest, [table], N=N, dscales=dscales, mode=mode)
+    out.copy_(table[:N * P].view(N, P))
     return out
+
+
+def round_prepare(delta_flags, bad_flags, round: int, active, n_active, w=None, init_w: bool = False, error_flag=None) -> None:
+    """Start of an averaging round on the device (no host sync): wait for every miner's publish flag, read the NaN verdicts
+    the miners attached to their publishes, write the ``active`` mask / count and optionally reset ``w`` to 1/n_active."""
+    N = active.numel()
+    P = w.shape[1] if w is not None else 0
+    _c(_lib.lib().dtb_round_prepare(_ptr_array([_dp(f) for f in delta_flags]) if delta_flags is not None else None,
+                                    _ptr_array([_dp(f) for f in bad_flags]) if bad_flags is not None else None,
+                                    ctypes.c_uint32(round), _lib.ptr(active), _lib.ptr(n_active), _lib.ptr(w), N, P, int(init_w),
+                                    _lib.ptr(error_flag), _lib.stream_ptr()), "round_prepare")
+    _tick()
+
+
+def shard_transpose(deltas, dscales, dsts, active, e0: int, e1: int, mode: int) -> None:
+    """Delta all-to-all by pull: ``dsts[i][0 : e1-e0] = fp32(deltas[i][e0 : e1])`` for every miner i in one launch."""
+    N = len(deltas)
+    _c(_lib.lib().dtb_shard_transpose(_ptr_array([_dp(d) for d in deltas]),
+                                      _ptr_array([_dp(x) for x in dscales]) if dscales is not None else None,
+                                      _ptr_array([_dp(d) for d in dsts]), _lib.ptr(active), ctypes.c_size_t(e0), ctypes.c_size_t(e1),
+                                      N, mode, _lib.num_sms() * 8, _lib.stream_ptr()), "shard_transpose")
+    _tick()
+
+
+def shard_pull16(srcs, manifest, chunks_per_rank: int, self_rank: int, dst, *, wait_flags=None, wait_value=0, error_flag=None) -> None:
+    """bf16 all-gather by pull: every chunk NOT owned by ``self_rank`` is copied from its owner's (peer-mapped) buffer."""
+    cs, cl, _ = manifest.seg_table(dst.device)
+    _c(_lib.lib().dtb_shard_pull16(_ptr_array([_dp(x) for x in srcs]),
+                                   _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None,
+                                   ctypes.c_uint32(wait_value), _lib.ptr(cs), _lib.ptr(cl), cs.numel(), chunks_per_rank, len(srcs),
+                                   self_rank, _lib.ptr(dst), _lib.ptr(error_flag), _lib.num_sms() * 8, _lib.stream_ptr()),
+       "shard_pull16")
+    _tick()
+
+
+def w_update(slots, w, lr: float, *, wait_flags=None, wait_value=0, loss_acc=None, error_flag=None) -> None:
+    """``w -= lr * sum_r slots[r]`` (tables of N*P + 1 floats, summed in a fixed order); the loss shares go to ``loss_acc``."""
+    N, P = w.shape
+    _c(_lib.lib().dtb_w_update(_ptr_array([_dp(x) for x in slots]),
+                               _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None,
+                               ctypes.c_uint32(wait_value), len(slots), _lib.ptr(w), ctypes.c_float(lr), N, P, _lib.ptr(loss_acc),
+                               _lib.ptr(error_flag), _lib.stream_ptr()), "w_update")
+    _tick()
+
+
+def set_flag_timeout(seconds: float) -> None:
+    """Bound of every device-side flag spin (default ~13 s); <= 0 waits forever."""
+    if have_kernels():
+        L = _lib.lib()
+        _c(L.dtb_set_flag_timeout_optim(ctypes.c_double(seconds)), "set_flag_timeout")
+        _c(L.dtb_set_flag_timeout_meta(ctypes.c_double(seconds)), "set_flag_timeout")
 
 
 def shard_pull_reset(shard_ptrs, manifest, chunks_per_rank, base_out, master, p16, m, v, *, reset_moments=True, wait_flags=None,

@@ -196,8 +196,9 @@ class PeerExchange(Exchange):
 
     kind = "peer"
 
-    def __init__(self, manifest: Manifest, group=None, delta_dtype: str = "fp32", with_base16: bool = True):
-        from .symm import F_BASE, F_DELTA, SymmetricWindow
+    def __init__(self, manifest: Manifest, group=None, delta_dtype: str = "fp32", with_base16: bool = True,
+                 with_meta: bool = True):
+        from .symm import F_BAD, F_BASE, F_DELTA, SymmetricWindow
 
         self.man = manifest
         self.delta_dtype_name = delta_dtype
@@ -210,9 +211,19 @@ class PeerExchange(Exchange):
         if with_base16:
             regions["base16"] = n * 2
         regions["w"] = 64 * len(manifest) * 4  # mixing matrix w[N<=64, P] shared by the averager
+        if with_meta:
+            # distributed learned mixer (parallel/meta.py): peer-readable validation gradient + per-rank meta-gradient tables
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.slot_words = (world * len(manifest) + 1 + 63) // 64 * 64
+            regions["g"] = n * 4
+            regions["gslot"] = world * self.slot_words * 4
+        self.with_meta = with_meta
         self.win = SymmetricWindow(regions, group)
         self.rank, self.world = self.win.rank, self.win.world
-        self.F_DELTA, self.F_BASE = F_DELTA, F_BASE
+        self.F_DELTA, self.F_BASE, self.F_BAD = F_DELTA, F_BASE, F_BAD
+        self._bad = torch.zeros(1, dtype=torch.int32, device=self.win.device)      # my delta holds NaN/Inf (set by the emit kernel)
+        self.active = torch.ones(max(self.world, 1), dtype=torch.int32, device=self.win.device)  # per-miner mask of the round
+        self.n_active = torch.zeros(1, dtype=torch.int32, device=self.win.device)
         self.nan_flags = torch.zeros(max(self.world, 1), dtype=torch.int32, device=self.win.device)
         self._base_round = 0
         self.with_base16 = with_base16
@@ -230,8 +241,14 @@ class PeerExchange(Exchange):
         return self.win.local(name, torch.float32) if rank is None else self.win.peer(name, rank, torch.float32)
 
     def publish_delta(self, trainer, round: int, dst_ranks: Optional[List[int]] = None) -> None:
-        """Delta is written straight into this rank's window (no copies), then the round flag is release-stored."""
-        trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round))
+        """Delta is written straight into this rank's window (no copies) while the emit kernel screens it for NaN/Inf;
+        the verdict (F_BAD slot = round iff bad) and then the round flag are release-stored into every peer's flag page."""
+        self._bad.zero_()
+        try:
+            trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round), self._bad)
+        except TypeError:  # adapters with the two-argument signature
+            trainer.emit_delta(self.delta_buf(round)[:self.man.total], self.scale_buf(round))
+        self.win.publish(self.F_BAD, round, dst_ranks, cond=self._bad)
         self.win.publish(self.F_DELTA, round, dst_ranks)
         self.win.heartbeat()  # liveness counter next to the round flag (failure detection, SURVEY 5.3)
 
@@ -276,7 +293,22 @@ class PeerExchange(Exchange):
             round = after  # a newer round landed while we copied: the buffer may be torn, take the newer one
         return None
 
+    def delta_is_bad(self, src: int, round: int) -> bool:
+        """Host read of the NaN verdict miner ``src`` attached to its publish of ``round``."""
+        return int(self.win.flags()[self.F_BAD + src].item()) == round
+
     # -- averager side ------------------------------------------------------------------------------------------------
+    def prepare_round(self, round: int, miners: Sequence[int], w: Optional[torch.Tensor] = None, init_w: bool = False) -> torch.Tensor:
+        """Stream-ordered start of an averaging round: wait for the miners' publish flags, collect their NaN verdicts into
+        ``self.active`` (int32 [len(miners)], 1 = take part) and optionally reset ``w`` to 1/n_active (reference: a NaN or
+        missing delta is skipped and ``w`` is rebuilt for the remaining miners, averaging_logic.py:396-430).  No host sync."""
+        df = [self.win.flag_ptr(self.F_DELTA + r) for r in miners]
+        bf = [self.win.flag_ptr(self.F_BAD + r) for r in miners]
+        self.active = self.active[:len(miners)] if self.active.numel() >= len(miners) else torch.ones(
+            len(miners), dtype=torch.int32, device=self.win.device)
+        ops.round_prepare(df, bf, round, self.active, self.n_active, w, init_w, self.win.error_flag)
+        return self.active
+
     def _delta_ptrs(self, round: int, miners: Sequence[int]) -> Tuple[List[int], Optional[List[int]]]:
         name, sname = f"delta{round & 1}", f"scale{round & 1}"
         d = [self.win.ptr(name, r) for r in miners]
@@ -284,7 +316,7 @@ class PeerExchange(Exchange):
         return d, s
 
     def gather_average(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int], out_f32,
-                       out_bf16=None, wait: bool = True) -> torch.Tensor:
+                       out_bf16=None, wait: bool = True, active: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Pull form of fused kernel (a): this rank reads every miner's delta over NVLink and writes theta_new locally."""
         d, s = self._delta_ptrs(round, miners)
         wf = [self.win.flag_ptr(self.F_DELTA + r) for r in miners] if wait else None
@@ -292,7 +324,7 @@ class PeerExchange(Exchange):
         mode = {"fp32": 0, "bf16": 1, "fp8": 2}[self.delta_dtype_name]
         return ops.weighted_avg(base, d, w, self.man, [out_f32], [out_bf16] if out_bf16 is not None else None, dscales=s,
                                 nan_flags=self.nan_flags, wait_flags=wf, wait_value=round, error_flag=self.win.error_flag,
-                                mode=mode)
+                                mode=mode, active=active)
 
     def sharded_average_broadcast(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int]) -> torch.Tensor:
         """Reduce-scatter + all-gather form: every rank reduces its shard of the arena from ALL miners' windows and
@@ -315,7 +347,8 @@ class PeerExchange(Exchange):
         self.win.wait(self.F_BASE, self._base_round)
         return self.win.local("base", torch.float32)[:self.man.total]
 
-    def reduce_scatter_average(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int]) -> int:
+    def reduce_scatter_average(self, base: torch.Tensor, w: torch.Tensor, round: int, miners: Sequence[int],
+                               active: Optional[torch.Tensor] = None) -> int:
         """Phase 1 of the pull-only round: this rank reduces ITS shard of the arena from all miners' windows (P2P loads)
         into its own base window and publishes the base flag.  Returns chunks_per_rank."""
         cs, _, _ = self.man.seg_table(base.device)
@@ -327,7 +360,8 @@ class PeerExchange(Exchange):
         self.nan_flags.zero_()
         mode = {"fp32": 0, "bf16": 1, "fp8": 2}[self.delta_dtype_name]
         ops.weighted_avg(base, d, w, self.man, [self.win.ptr("base", self.rank)], None, dscales=s, nan_flags=self.nan_flags,
-                         wait_flags=wf, wait_value=round, error_flag=self.win.error_flag, chunk_range=(c0, c1), mode=mode)
+                         wait_flags=wf, wait_value=round, error_flag=self.win.error_flag, chunk_range=(c0, c1), mode=mode,
+                         active=active)
         self._base_round = round + 1
         self.win.publish(self.F_BASE, self._base_round)
         return per

@@ -27,6 +27,10 @@ F_BASE = 64     # [F_BASE + src]   = last base round pushed by averager-shard sr
 F_BARRIER = 128  # [F_BARRIER + src] = barrier epoch
 F_HEART = 192   # [F_HEART + src]  = averager's mixing-matrix epoch (w broadcast)
 F_ALIVE = 256   # [F_ALIVE + src]  = liveness heartbeat counter (failure detection)
+F_TB = 320      # [F_TB + src]     = meta tick whose theta_bar bf16 shard rank src has completed
+F_G = 384       # [F_G + src]      = meta tick whose validation gradient rank src has completed (data-parallel mode)
+F_GP = 448      # [F_GP + src]     = meta tick whose meta-gradient partial rank src has stored into my slot table
+F_BAD = 512     # [F_BAD + src]    = round whose delta from miner src holds NaN/Inf (0 / older round = clean)
 
 
 class _CudaBuffer:
@@ -116,12 +120,14 @@ class SymmetricWindow:
         return self.local("flags", torch.int32)
 
     # -- synchronisation -------------------------------------------------------------------------------------------
-    def publish(self, block: int, value: int, dst_ranks: Optional[List[int]] = None) -> None:
+    def publish(self, block: int, value: int, dst_ranks: Optional[List[int]] = None, cond: Optional[torch.Tensor] = None) -> None:
         """After all prior work on the current stream: release-store ``value`` into slot [block + my_rank] of every
-        destination rank's flag page (csrc/optim_avg.cu publish_flag_kernel)."""
+        destination rank's flag page (csrc/optim_avg.cu publish_flag_kernel).  ``cond`` (device int32[1]): store ``value``
+        only if it is non-zero, else 0 (a verdict computed on the device travels without a host read)."""
         dst = list(range(self.world)) if dst_ranks is None else dst_ranks
         arr = (ctypes.c_void_p * len(dst))(*[self.flag_ptr(block + self.rank, r) for r in dst])
-        _lib.check(_lib.lib().dtb_publish_flag(arr, len(dst), ctypes.c_uint32(value), _lib.stream_ptr()), "publish_flag")
+        _lib.check(_lib.lib().dtb_publish_flag(arr, len(dst), ctypes.c_uint32(value), _lib.stream_ptr(), _lib.ptr(cond)),
+                   "publish_flag")
 
     def wait(self, block: int, value: int, src_ranks: Optional[List[int]] = None) -> None:
         """Stream-ordered wait (device-side spin) until slot [block + src] >= value for every src."""
@@ -154,8 +160,25 @@ class SymmetricWindow:
         return [r for r, v in enumerate(f) if r != self.rank and v < min_beat]
 
     def check_errors(self) -> None:
+        """Blocking check (one host sync): raise if any device-side flag wait of this rank timed out."""
         if int(self.error_flag.item()) != 0:
             raise RuntimeError("peer flag wait timed out (a rank stalled or died)")
+
+    def poll_errors(self) -> None:
+        """NON-blocking check for the hot path (once per round): the error flag is copied to pinned host memory behind the
+        work queued so far; a copy that has completed by a later call is inspected then.  A timed-out wait therefore raises
+        one round late instead of forcing a host sync into every stream-ordered round."""
+        pend = getattr(self, "_err_pending", None)
+        if pend is not None and pend[1].query():
+            if int(pend[0].item()) != 0:
+                raise RuntimeError("peer flag wait timed out (a rank stalled or died)")
+            pend = None
+        if pend is None:
+            host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            host.copy_(self.error_flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._err_pending = (host, ev)
 
     def close(self) -> None:
         L = _lib.lib()

@@ -179,8 +179,10 @@ class _FlatAsDelta:
     def __init__(self, flat):
         self.flat, self.master = flat, flat
 
-    def emit_delta(self, out, scales=None):
+    def emit_delta(self, out, scales=None, bad=None):
         out.copy_(self.flat.to(out.dtype))
+        if bad is not None and not bool(torch.isfinite(self.flat).all()):
+            bad.fill_(1)
         return out
 
 

@@ -17,7 +17,7 @@ class _FlatDelta:
     def __init__(self, flat):
         self.flat, self.master = flat, flat
 
-    def emit_delta(self, out, scales=None):
+    def emit_delta(self, out, scales=None, bad=None):
         out[: self.flat.numel()].copy_(self.flat.to(out.dtype))
         return out
 

@@ -41,10 +41,16 @@ class FaultyExchange:
         if "nan" in self._faults:
             class _NaN:
                 master = trainer.master
-                def emit_delta(_, out, scales=None):
-                    trainer.emit_delta(out, scales)
-                    if out.dtype != torch.uint8:
-                        out.view(-1)[out.numel() // 3] = float("nan")
+                def emit_delta(_, out, scales=None, bad=None):
+                    # poison one MASTER element for the duration of the emit so that the delta kernel's own NaN screen
+                    # (the verdict that travels with the publish flag) sees it, exactly like a diverged miner would
+                    k = trainer.master.numel() // 3
+                    keep = trainer.master[k].clone()
+                    trainer.master[k] = float("nan")
+                    try:
+                        trainer.emit_delta(out, scales, bad) if bad is not None else trainer.emit_delta(out, scales)
+                    finally:
+                        trainer.master[k] = keep
                     return out
             return self._ex.publish_delta(_NaN(), round, *a, **kw)
         return self._ex.publish_delta(trainer, round, *a, **kw)
