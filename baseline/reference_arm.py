@@ -156,28 +156,39 @@ def run_reference(args) -> dict:
         lens = ((1.0 - 0.25 * torch.rand(B, generator=g)) * T).long().clamp_(1, T)
         mask = torch.arange(T)[None, :] < lens[:, None]
         ids = torch.where(mask, ids, torch.full_like(ids, 50257))
-        pool.append({"input_ids": ids, "attention_mask": mask.long(), "labels": ids.clone()})
+        # PINNED host memory: every step's ``.to(device)`` in the reference loop (training_manager.py:381-383) is then a real
+        # asynchronous PCIe transfer, as the end-to-end rule of the bench contract asks
+        pool.append({k: v.pin_memory() for k, v in {"input_ids": ids, "attention_mask": mask.long(), "labels": ids.clone()}.items()})
 
     hub = DiskHubStub(os.path.join(work, f"hub_rank{rank}"))
     events = {}
 
     class TimedLoader:
-        """W warm-up batches, then exactly K timed batches; flips ``send_interval`` so that ONE delta push (torch.save of
-        weight_diff.pt + hub push) happens right after the last timed step, inside the timed region."""
+        """W warm-up batches, then TWO separately timed regions of exactly K batches each (``value`` and ``e2e``: the
+        reference has a single mode -- pinned-host batch -> ``.to(device)`` x3 -> step -> ``loss.item()`` -- so both regions
+        run the same end-to-end loop, measured independently).  ``send_interval`` is flipped so that ONE delta push
+        (torch.save of weight_diff.pt + hub push) happens right after the last step of EACH region, inside it."""
 
         def __init__(self):
             self.loop = None
 
+        def _mark(self, name):
+            if world > 1:
+                dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+            events[name] = torch.cuda.Event(enable_timing=True)
+            events[name].record()
+
         def __iter__(self):
-            for i in range(W + K):
+            n_regions = 1 if args.no_e2e else 2
+            for i in range(W + n_regions * K):
                 if i == W:
-                    if world > 1:
-                        dist.barrier(device_ids=[local])
-                    torch.cuda.synchronize()
-                    events["e0"] = torch.cuda.Event(enable_timing=True)
-                    events["e1"] = torch.cuda.Event(enable_timing=True)
-                    events["e0"].record()
-                if i == W + K - 1:
+                    self._mark("e0")
+                if i == W + K:  # the push of region 1 ran after step W+K-1: close region 1, open region 2
+                    self._mark("e1")
+                    self.loop.send_interval = 1e12
+                    self._mark("f0")
+                if i in (W + K - 1, W + 2 * K - 1):
                     self.loop.send_interval = 0.0
                 yield pool[i % len(pool)]
 
@@ -190,26 +201,36 @@ def run_reference(args) -> dict:
     sampler = ClockSampler(local)
     sampler.start()
     loop.train(1)
-    events["e1"].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier(device_ids=[local])
+    loader._mark("f1" if not args.no_e2e else "e1")
     clocks = sampler.stop()
-    ms = events["e0"].elapsed_time(events["e1"])
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
+
+    def mx(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        return float(t.item())
+
+    ms = mx(events["e0"].elapsed_time(events["e1"]))
+    ms_e2e = mx(events["f0"].elapsed_time(events["f1"])) if not args.no_e2e else None
+    if world > 1:
         dist.destroy_process_group()
     tokens = K * B * T * world
+    from bench import GPT2_SMALL_DESC, shared_config
     out = {
         "impl": "reference", "metric": "tokens/sec (GPT-2-small local-SGD training, all miners; per-miner = value / n_gpus)",
         "value": tokens / ms * 1e3, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (the reference's only precision)",
         "data": "synthetic tokens (Zipf ids, right-padded), random-init weights",
-        "config": {"model": f"GPT2LMHeadModel + [PAD] ({nparams} params)", "global_batch": B * world, "micro_batch_per_miner": B,
-                   "seq_len": T, "parallelism": f"{world} independent reference miners", "delta_pushes_in_timed_region": hub.pushes,
-                   "api": "hivetrain.training_manager.DeltaLoop.train (unmodified, baseline/_ref)"},
+        "config": shared_config(GPT2_SMALL_DESC, B, T, world),
+        "detail": {"model": f"transformers.GPT2LMHeadModel + [PAD] ({nparams} params), fp32 eager",
+                   "parallelism": f"{world} independent reference miners (upstream has no multi-GPU mode; no averager in this arm)",
+                   "delta_pushes": hub.pushes, "api": "hivetrain.training_manager.DeltaLoop.train (unmodified, baseline/_ref)"},
         "clocks": clocks, "gpu_launches": 0,
     }
+    if ms_e2e is not None:
+        # per step: 3 pinned int64 [B,T] tensors host->device (input_ids, attention_mask, labels), loss.item() device->host
+        out["e2e"] = {"value": tokens / ms_e2e * 1e3, "unit": "tokens/s", "ms_per_step": ms_e2e / K,
+                      "h2d_bytes_per_step": 3 * B * T * 8, "d2h_bytes_per_step": 4,
+                      "api": "hivetrain.training_manager.DeltaLoop.train (separately timed second region of K steps)"}
     return out if rank == 0 else {}

@@ -14,7 +14,11 @@ Two timed regions of exactly K steps each (both bracketed by barrier + cuda sync
   * ``value``: inputs already resident on the device (kernel/collective time only);
   * ``e2e``:   through the public API (``training_manager.DeltaLoop.train``): every step copies its input batch from
                pinned host memory and copies the step's loss back to pinned host memory.
-Every timed region performs at least one full averaging round.  Data: synthetic tokens; weights: random init.
+Every timed region performs at least one averaging round (with ``--meta-steps`` learned-mixer steps).  A third region
+(``full_round``) measures ONE WHOLE ROUND directly: ``--local-steps`` optimizer steps + the reference-faithful learned mixer
+(``--meta-epochs``^2 passes over ``--val-texts`` sequences @ ``--val-seq``, run by all ranks) + averaging + base broadcast.
+Data: synthetic tokens; weights: random init.  ``--impl reference`` = the unmodified upstream miner, ``--impl torch-bf16`` = HF
+GPT-2 under bf16 autocast + SDPA + fused AdamW + NCCL round (the strongest stock-library baseline).
 """
 from __future__ import annotations
 
@@ -36,18 +40,37 @@ def parse_args(argv=None):
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl", "nvls"])
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl", "nvls", "torch-bf16"])
     ap.add_argument("--model", type=str, default="gpt2")
     ap.add_argument("--batch-size", type=int, default=512, help="sequences per miner per step (both arms use the same default)")
     ap.add_argument("--seq-len", type=int, default=64, help="reference miner sequence length (neurons/miner.py:70)")
     ap.add_argument("--local-steps", type=int, default=100)
-    ap.add_argument("--meta-steps", type=int, default=1, help="learned-mixer SGD steps per round on the averager rank")
+    ap.add_argument("--meta-steps", type=int, default=1, help="learned-mixer SGD steps in the rounds of the K-step timed regions")
+    ap.add_argument("--meta-epochs", type=int, default=7, help="full-round region: meta_epochs^2 passes over the validation set "
+                    "(reference neurons/averager.py:106: 7)")
+    ap.add_argument("--val-texts", type=int, default=100, help="validation sequences (reference neurons/averager.py:61)")
+    ap.add_argument("--val-seq", type=int, default=512, help="validation sequence length (reference neurons/averager.py:72)")
+    ap.add_argument("--val-batch", type=int, default=8, help="averager batch size (reference: --batch_size; validator uses 8)")
+    ap.add_argument("--meta-mode", type=str, default="auto", choices=["auto", "replicate", "dp"])
+    ap.add_argument("--no-full-round", action="store_true", help="skip the directly measured whole round (100 local steps + "
+                    "reference-faithful meta-learning + averaging)")
     ap.add_argument("--delta-dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp8"])
     ap.add_argument("--lr", type=float, default=5e-4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dropout", type=float, default=None, help="train-mode dropout; default = the model preset (GPT-2: 0.1, as in the reference)")
     ap.add_argument("--fp8-forward", action="store_true", help="e4m3 forward GEMMs with delayed scaling (config 4)")
     return ap.parse_args(argv)
+
+
+def shared_config(model_desc: str, B: int, T: int, world: int) -> dict:
+    """``config`` block emitted IDENTICALLY by every arm (ours / reference / torch-bf16 / nccl): what is being measured.
+    Arm-specific details live in the top-level ``detail`` key."""
+    return {"model": model_desc, "global_batch": B * world, "micro_batch_per_miner": B, "seq_len": T,
+            "parallelism": f"dp{world} (one miner per GPU, local-SGD delta averaging)",
+            "l2_policy": "per-step working set (>= 2 GB of weights, optimizer state and activations) >> 126 MB L2"}
+
+
+GPT2_SMALL_DESC = "gpt2-small + [PAD] (124440576 params, vocab 50258)"
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -126,12 +149,13 @@ def run_ours(args) -> dict:
     assert device.type == "cuda", "bench.py needs a GPU"
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     B, T, K, W = args.batch_size, args.seq_len, args.steps, args.warmup
-    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0,  # same theta_base on every rank
+    # seed=0: the same theta_base on every rank; dropout_seed=rank: independent dropout masks per miner
+    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0, dropout_seed=rank,
                       fp8_forward=args.fp8_forward, dropout=args.dropout)
     V = trainer.cfg.vocab_size
     if args.impl == "nccl":
         ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
-        plane = "nccl all_gather + torch weighted sum" if world > 1 else "local torch"
+        plane = "nccl all_gather / all_reduce + torch" if world > 1 else "local torch"
     elif args.impl == "nvls" and world > 1:
         from distributedtraining_b200.parallel.exchange import NvlsExchange
         ex = NvlsExchange(trainer.man)  # uniform mixer: in-switch reduction + multicast of the new base
@@ -139,19 +163,25 @@ def run_ours(args) -> dict:
         args.meta_steps = 0
     else:
         ex = PeerExchange(trainer.man, delta_dtype=args.delta_dtype)
-        plane = "peer windows (fused gather-avg-broadcast kernel)"
+        plane = "peer windows (sharded fused gather-avg kernels + pull all-gather, no NCCL)"
     dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
     host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
-    val = SyntheticTokens(B, T, V, seed=7, device=str(device), pool=2)
-    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps, mixer="uniform" if args.impl == "nvls" else "learned",
-                                val_batches=[b["input_ids"] for b in val.pool], post_pull_lr=5e-5)
+    # validation set of the averager: ``val_texts`` sequences @ ``val_seq`` in batches of ``val_batch`` (the last one smaller),
+    # identical on every rank (reference neurons/averager.py:58-94)
+    Tv = min(args.val_seq, trainer.cfg.n_positions)
+    Bv = min(args.val_batch, args.val_texts)
+    vs = SyntheticTokens(args.val_texts, Tv, V, seed=7, device=str(device), pool=1).pool[0]
+    val = [{k: v[i:i + Bv] for k, v in vs.items()} for i in range(0, args.val_texts, Bv)]
+    learned = args.impl != "nvls"
+    coord = LocalSGDCoordinator(trainer, ex, meta_steps=args.meta_steps, mixer="learned" if learned else "uniform",
+                                val_batches=val, post_pull_lr=5e-5, meta_mode=args.meta_mode)
     # the optimizer keeps lr=5e-4 in round 0 and 5e-5 after the first pull, as in the reference miner
 
     def run_steps(n: int, pool, gstep0: int, force_round: bool) -> int:
         g = gstep0
         did_round = False
         for i in range(n):
-            trainer.step(pool[i % len(pool)]["input_ids"])
+            trainer.step(pool[i % len(pool)])  # dict batch: input_ids + kv_len (padding mask); labels = input_ids
             g += 1
             if g % args.local_steps == 0:
                 coord.finish_round()
@@ -183,29 +213,22 @@ def run_ours(args) -> dict:
     eager_launches = ops.launch_count() - c0
     launches = K * trainer.launches_per_step + (eager_launches if trainer.use_graph else eager_launches - K * trainer.launches_per_step)
     tokens = K * B * T * world
+    desc = GPT2_SMALL_DESC if trainer.cfg.name == "gpt2" else f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})"
     result = {
         "metric": "tokens/sec (GPT-2-small local-SGD training, all miners; per-miner = value / n_gpus)",
         "value": tokens / ms_total * 1e3, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic tokens (Zipf ids, right-padded), random-init weights", "impl": args.impl,
         "tokens_per_s_per_miner": tokens / ms_total * 1e3 / world, "rounds_in_timed_region": rounds,
-        "avg_round_ms": ms_total / max(rounds, 1),
-        "config": {"model": f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})", "global_batch": B * world,
-                   "micro_batch_per_miner": B, "seq_len": T, "parallelism": f"local-sgd dp{world}", "local_steps": args.local_steps,
-                   "meta_steps_per_round": coord.meta_steps, "delta_dtype": args.delta_dtype, "exchange": plane,
-                   "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward), "dropout": trainer.cfg.dropout, "cuda_graph": bool(trainer.use_graph),
-                   "l2_policy": "per-step working set (weights 0.25 GB bf16 + 1.5 GB fp32 state + ~5 GB activations) >> 126 MB L2"},
+        "config": shared_config(desc, B, T, world),
+        "detail": {"local_steps": args.local_steps, "meta_steps_in_timed_rounds": coord.meta_steps, "delta_dtype": args.delta_dtype,
+                   "exchange": plane, "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward),
+                   "dropout": trainer.cfg.dropout, "padding_mask": "attention_mask -> kv_len in the attention kernels",
+                   "cuda_graph": bool(trainer.use_graph),
+                   "meta": coord.meta.describe() if coord.meta is not None else None},
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},
     }
-    # avg-round wall time (BASELINE.json's second metric) for the configured cadence: local_steps optimizer steps + one
-    # exchange; measured directly when the timed region spans whole rounds, projected from the per-step and per-exchange
-    # device times otherwise (a short K with one forced round)
-    exch_ms = sum(phases.values()) / max(rounds, 1)
-    step_ms = (ms_total - exch_ms * rounds) / K
-    result["round_ms_at_local_steps"] = {"local_steps": args.local_steps, "exchange_ms": round(exch_ms, 3),
-                                         "step_ms": round(step_ms, 3), "round_ms": round(args.local_steps * step_ms + exch_ms, 2),
-                                         "measured_directly": bool(K % args.local_steps == 0 and K >= args.local_steps)}
     # ---- region 2: end to end through the public API (pinned-host inputs, per-step loss read-back) ----
     if not args.no_e2e:
         loop = DeltaLoop(device, args.model, host_data, learning_rate=args.lr, hf_manager=None, trainer=trainer,
@@ -221,8 +244,51 @@ def run_ours(args) -> dict:
         barrier_sync(device)
         ms_e2e = max_over_ranks(e0.elapsed_time(e1), device)
         result["e2e"] = {"value": tokens / ms_e2e * 1e3, "unit": "tokens/s", "ms_per_step": ms_e2e / K,
-                         "h2d_bytes_per_step": B * T * 4, "d2h_bytes_per_step": 4, "api": "training_manager.DeltaLoop.train",
-                         "last_loss": float(loop.host_losses[-1]) if loop.host_losses is not None else None}
+                         "h2d_bytes_per_step": host_data.bytes_per_batch, "d2h_bytes_per_step": 4,
+                         "api": "training_manager.DeltaLoop.train",
+                         "last_loss": float(loop.host_losses[(K - 1) % loop.host_losses.numel()]) if loop.host_losses is not None else None}
+        coord.timer.summary()
+    # ---- region 3: ONE WHOLE ROUND measured directly (BASELINE.json's second metric, avg-round wall time): local_steps
+    # optimizer steps, delta emit, the reference-faithful learned mixer (meta_epochs^2 passes over val_texts sequences @ val_seq,
+    # hivetrain/averaging_logic.py:490-541 + neurons/averager.py:106) executed by all ranks, averaging, base broadcast + reset ----
+    if not args.no_full_round and learned and (world == 1 or ex is not None):
+        coord.meta_epochs = args.meta_epochs
+        nsteps_meta = args.meta_epochs ** 2 * len(val)
+        barrier_sync(device)
+        m0 = coord.meta_steps_done
+        e0.record()
+        for i in range(args.local_steps):
+            trainer.step(dev_data.pool[i % len(dev_data.pool)])
+        em = torch.cuda.Event(enable_timing=True)
+        em.record()
+        coord.finish_round()
+        e1.record()
+        barrier_sync(device)
+        ms_round = max_over_ranks(e0.elapsed_time(e1), device)
+        ms_mine = max_over_ranks(e0.elapsed_time(em), device)
+        ph = coord.timer.summary()
+        coord.meta_epochs = 0
+        done = coord.meta_steps_done - m0
+        result["full_round"] = {
+            "measured_directly": True, "round_ms": round(ms_round, 2), "local_steps": args.local_steps,
+            "mining_ms": round(ms_mine, 2), "exchange_ms": round(ms_round - ms_mine, 2), "meta_epochs": args.meta_epochs,
+            "meta_steps": int(done), "meta_steps_expected": int(nsteps_meta),
+            "ms_per_meta_step": round(max_over_ranks(ph.get("meta_learning", 0.0), device) / max(done, 1), 4),
+            "phase_ms_rank0": {k: round(v, 3) for k, v in ph.items()},
+            "val_set": {"texts": args.val_texts, "seq": Tv, "batch": Bv, "batches": len(val)},
+            "tokens_per_s_incl_averaging": round(args.local_steps * B * T * world / ms_round * 1e3, 1),
+            "val_loss_last_step": float(coord.meta.loss_acc[1]) if coord.meta is not None else None,
+            "w_mean_per_miner": [round(float(x), 5) for x in coord.w.mean(dim=1)]}
+    # ---- cross-rank agreement: every rank must hold the same base after the rounds above ----
+    cks = ops.checksum(trainer.base)
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, cks)
+    else:
+        allc = [cks]
+    result["base_checksum"] = {"rank0": allc[0], "identical_on_all_ranks": bool(all(c == allc[0] for c in allc))}
+    if hasattr(ex, "win"):
+        ex.win.check_errors()
     if dist.is_initialized():
         dist.destroy_process_group()
     return result if rank == 0 else {}
@@ -234,6 +300,13 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         from baseline.reference_arm import run_reference
         out = run_reference(args)
+        if out:
+            print(json.dumps(out), flush=True)
+        return
+    if args.impl == "torch-bf16":
+        maybe_respawn(args)
+        from baseline.torch_bf16_arm import run_torch_bf16
+        out = run_torch_bf16(args)
         if out:
             print(json.dumps(out), flush=True)
         return

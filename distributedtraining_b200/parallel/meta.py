@@ -55,7 +55,8 @@ class DistributedMetaLearner:
         self.dev = trainer.master.device
         self.val_batches = [self._norm_batch(b) for b in (val_batches or [])]
         assert self.val_batches, "the learned mixer needs validation batches"
-        self.Bv, self.Tv = self.val_batches[0]["input_ids"].shape
+        self.Bv = max(int(b["input_ids"].shape[0]) for b in self.val_batches)
+        self.Tv = int(self.val_batches[0]["input_ids"].shape[1])
         if mode == "auto":  # data-parallel only when every rank gets enough rows to keep its GEMMs busy
             mode = "dp" if (self.world > 1 and self.Bv >= 4 * self.world) else "replicate"
         if self.world == 1:
@@ -84,10 +85,8 @@ class DistributedMetaLearner:
         else:
             self.g = torch.zeros(man.total, **f32)
         self.engine = TransformerEngine(trainer.cfg, man, trainer.p16, self.g, rows_static, self.Tv, seed=1234 + self.rank)
-        if mode == "dp":
-            self.engine.loss_denominator = self.Bv * (self.Tv - 1)  # sum over ranks of the local gradients = the batch gradient
         self.use_graph = (self.dev.type == "cuda") if use_graph is None else (use_graph and self.dev.type == "cuda")
-        self._graph = None
+        self._graphs = {}
         if self.peer:
             self._dT_ptrs = [self.dT[i].data_ptr() - 4 * self.e0 for i in range(self.N)]  # virtual bases: element e at ptr + 4e
             self._partial = torch.empty(max(self.c1 - self.c0, 1) * (self.N + 1), **f32)
@@ -144,20 +143,30 @@ class DistributedMetaLearner:
         if not self.use_graph:
             e.forward_backward(True, dropout=self.meta_dropout)
             return
-        if self._graph is None:  # eager warm-up on a side stream, then capture (same protocol as Trainer.step)
+        # the CE normaliser (1 / valid tokens) is a kernel ARGUMENT, so a captured graph is only valid for one
+        # (row count, denominator) pair: one graph per distinct pair (the last validation batch is usually smaller)
+        key = (e.n_rows, e.loss_denominator)
+        g = self._graphs.get(key)
+        if g is None:  # eager warm-up on a side stream, then capture (same protocol as Trainer.step)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 e.forward_backward(True, dropout=self.meta_dropout)
             torch.cuda.current_stream().wait_stream(s)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
                 e.forward_backward(True, dropout=self.meta_dropout)
-        self._graph.replay()
+            self._graphs[key] = g
+        g.replay()
 
     def _set_batch(self, k: int) -> None:
         b = self.val_batches[k % len(self.val_batches)]
-        r0, r1 = self.r0, self.r1
+        bsz = b["input_ids"].shape[0]
+        if self.mode == "dp":  # rows of THIS batch owned by this rank; gradients are normalised by the batch's global token count
+            r0, r1 = _rows_of(bsz, self.world, self.rank)
+            self.engine.loss_denominator = bsz * (self.Tv - 1)
+        else:
+            r0, r1 = 0, bsz
         kv = b.get("kv_len")
         self.engine.set_batch(b["input_ids"][r0:r1], b["labels"][r0:r1], None, kv[r0:r1] if kv is not None else None)
 

@@ -156,7 +156,7 @@ class TrainingLoop:
             for step, batch in enumerate(self.data_loader):
                 if self._due_poll():
                     self._maybe_pull()
-                loss = self.model.step(_ids_of(batch))
+                loss = self.model.step(batch if isinstance(batch, dict) and hasattr(self.model, "engine") else _ids_of(batch))
                 agg.add_(self.model.grad)
                 self._loss_acc += loss
                 self._loss_n += 1
@@ -199,7 +199,9 @@ class DeltaLoop(TrainingLoop):
             for step, batch in enumerate(self.data_loader):
                 if self._due_poll():
                     self._maybe_pull()
-                loss = m.step(_ids_of(batch), _labels_of(batch))
+                # dict batches go through whole: the engine reads input_ids (labels = input_ids, PAD not masked) and applies the
+                # attention_mask as padding mask, as the reference's model(...) call does (:380-384)
+                loss = m.step(batch if isinstance(batch, dict) and hasattr(m, "engine") else _ids_of(batch), _labels_of(batch))
                 if self.host_losses is not None:
                     self.host_losses[self.global_step % self.host_losses.numel()].copy_(loss, non_blocking=True)
                 self._loss_acc += loss

@@ -54,3 +54,18 @@ def test_nvls_plane_matches_allreduce_reference():
     if "nvls" in out:
         pytest.skip(out["nvls"])
     assert out["all_ranks_ok"], out
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_distributed_meta_learner_peer_vs_nccl_vs_sequential():
+    """The sharded learned mixer over peer windows (csrc/meta_avg.cu) == its NCCL formulation == the sequential one-rank
+    reference loop; w bit-identical on every rank."""
+    n = min(_ngpu(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29614", os.path.join(ROOT, "scripts", "meta_check.py"), "--model", "gpt2-tiny",
+                        "--val-batch", "9", "--val-seq", "64", "--steps", "6"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("META_CHECK ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    out = json.loads(line[-1][len("META_CHECK "):])
+    assert out["all_ranks_ok"] and out["w_moved"] > 0, out

@@ -427,3 +427,133 @@ def test_gemm_two_sm_pairs_with_odd_tile_count(epi):
     _close(out, r, rtol=1e-2)
     if epi == "bias_gelu":
         _close(out2, r2, rtol=1e-2)
+
+
+def test_meta_kernels_single_gpu():
+    """csrc/meta_avg.cu on one device against plain torch: delta shard transpose (fp32/bf16/fp8), active-mask weighted
+    average, segmented multi-dot with R summed gradient arenas over a chunk range, w update from slot tables."""
+    torch.manual_seed(11)
+    man = _toy_manifest()
+    n, P, N = man.total, len(man), 5
+    tid = man.tensor_ids(DEV)
+    cs, cl, _ = man.seg_table("cpu")
+    nch = cs.numel()
+    c0, c1 = nch // 3, nch - 1
+    e0, e1 = int(cs[c0]), int(cs[c1 - 1]) + int(cl[c1 - 1])
+    base = torch.randn(n, device=DEV)
+    true = [torch.randn(n, device=DEV) * 0.1 for _ in range(N)]
+    active = torch.tensor([1, 1, 0, 1, 1], dtype=torch.int32, device=DEV)
+    # ---- transpose: typed windows -> local fp32 shards (inactive miners -> zeros) ----
+    for mode, name in [(0, "fp32"), (1, "bf16"), (2, "fp8")]:
+        scales = None
+        if name == "fp32":
+            srcs, dec = true, true
+        elif name == "bf16":
+            srcs = [t.bfloat16() for t in true]
+            dec = [s.float() for s in srcs]
+        else:
+            srcs, scales = [], []
+            for t in true:
+                q, sc = torch.empty(n, device=DEV, dtype=torch.uint8), torch.empty(n // 32, device=DEV)
+                ops.delta_emit(t, torch.zeros_like(t), q, sc)
+                srcs.append(q); scales.append(sc)
+            dec = [ops.dequant_fp8(q, s) for q, s in zip(srcs, scales)]
+        dT = torch.full((N, e1 - e0), 7.0, device=DEV)
+        ops.shard_transpose(srcs, scales, [dT[i] for i in range(N)], active, e0, e1, mode)
+        for i in range(N):
+            want = dec[i][e0:e1] if int(active[i]) else torch.zeros(e1 - e0, device=DEV)
+            assert torch.equal(dT[i], want), (name, i)
+    # ---- active-mask weighted average over the shard, from virtual (global-index) pointers ----
+    dT = torch.stack([t[e0:e1].clone() for t in true])
+    dT[2] = float("nan")  # an inactive miner's data must never be touched
+    vptr = [dT[i].data_ptr() - 4 * e0 for i in range(N)]
+    w = torch.rand(N, P, device=DEV) - 0.2
+    out = torch.zeros(n, device=DEV)
+    out16 = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    ops.weighted_avg(base, vptr, w, man, [out], [out16], chunk_range=(c0, c1), mode=0, active=active)
+    keep = [0, 1, 3, 4]
+    want = base * w[keep].sum(0)[tid] + sum(w[i][tid] * true[i] for i in keep)
+    _close(out[e0:e1], want[e0:e1], rtol=1e-5)
+    _close(out16[e0:e1], want[e0:e1], rtol=1e-2)
+    assert float(out[:e0].abs().max()) == 0.0 and float(out[e1:].abs().max()) == 0.0
+    # ---- segmented multi-dot: 3 gradient arenas summed with scales, chunk range, two destination tables ----
+    gs = [torch.randn(n, device=DEV) for _ in range(3)]
+    gsc = [0.5, 0.25, 2.0]
+    loss = torch.tensor(3.25, device=DEV)
+    tabs = [torch.full((N * P + 1,), -1.0, device=DEV) for _ in range(2)]
+    dT[2] = 0.0
+    ops.seg_dot(gs, vptr, base, out, man, tabs, N=N, gscales=gsc, chunk_range=(c0, c1), active=active, loss=loss, loss_scale=0.5)
+    gsum = sum(s * g for s, g in zip(gsc, gs))
+    sel = torch.zeros(n, dtype=torch.bool, device=DEV)
+    sel[e0:e1] = True
+    rG = torch.zeros(N, P, device=DEV)
+    for i in range(N):
+        if int(active[i]):
+            rG[i].index_add_(0, tid[sel], (gsum * (true[i] + base - out))[sel])
+    for tb in tabs:
+        _close(tb[:N * P].view(N, P), rG, rtol=2e-3)
+        assert float(tb[N * P]) == 3.25 * 0.5
+    assert torch.equal(tabs[0], tabs[1])
+    # ---- w update: fixed-order sum of the slot tables ----
+    w0 = w.clone()
+    acc = torch.zeros(2, device=DEV)
+    ops.w_update(tabs, w, 0.01, loss_acc=acc)
+    _close(w, w0 - 0.01 * 2 * tabs[0][:N * P].view(N, P), rtol=1e-5)
+    assert float(acc[0]) == 3.25 and float(acc[1]) == 3.25
+    # ---- round prepare: flags already satisfied, NaN verdict of miner 1 ----
+    flags = torch.zeros(64, dtype=torch.int32, device=DEV)
+    flags[:N] = 4            # publish flags: round 4
+    flags[32 + 1] = 4        # miner 1 flagged its round-4 delta as bad
+    flags[32 + 3] = 3        # an OLD verdict of miner 3 does not count
+    act, nact = torch.zeros(N, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    w2 = torch.zeros(N, P, device=DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.round_prepare([flags.data_ptr() + 4 * i for i in range(N)], [flags.data_ptr() + 4 * (32 + i) for i in range(N)], 4, act, nact,
+                      w2, True, err)
+    assert act.tolist() == [1, 0, 1, 1, 1] and int(nact) == 4 and int(err) == 0
+    assert torch.equal(w2[0], torch.full((P,), 0.25, device=DEV)) and float(w2[1].abs().max()) == 0.0
+
+
+def test_peer_meta_learner_world1_matches_sequential():
+    """DistributedMetaLearner on the peer back-end with a single rank (no torch.distributed): every kernel of the step
+    sequence runs (windows, flags, transposes, slots) and must reproduce the sequential reference loop."""
+    from distributedtraining_b200.models.trainer import Trainer
+    from distributedtraining_b200.parallel.exchange import PeerExchange
+    from distributedtraining_b200.parallel.meta import DistributedMetaLearner
+    torch.manual_seed(3)
+    tr = Trainer("gpt2-tiny", device=DEV, batch=8, seq=64, lr=1e-3, seed=0, use_graph=False)
+    for _ in range(3):
+        tr.step(torch.randint(0, tr.cfg.vocab_size - 1, (8, 64), dtype=torch.int32, device=DEV))
+    ex = PeerExchange(tr.man)
+    ex.publish_delta(tr, 1)
+    delta = (tr.master - tr.base).clone()
+    V = tr.cfg.vocab_size
+    val = []
+    for s in range(2):
+        ids = torch.randint(0, V - 1, (4, 64), dtype=torch.int32, device=DEV)
+        kv = torch.tensor([64, 20, 1, 50], dtype=torch.int32, device=DEV)
+        val.append({"input_ids": ids, "labels": ids.clone(), "kv_len": kv})
+    t2 = Trainer(tr.cfg, device=DEV, batch=8, seq=64, seed=0, init_flat=tr.base.clone(), use_graph=False)
+    ml = DistributedMetaLearner(t2, ex, [0], val, meta_lr=0.05)
+    ml.begin_round(1)
+    ml.run(2)
+    ref_t = Trainer(tr.cfg, device=DEV, batch=4, seq=64, seed=0, init_flat=tr.base.clone(), use_graph=False)
+    P = len(tr.man)
+    w = torch.ones(1, P, device=DEV)
+    G = torch.empty(1, P, device=DEV)
+    for _ in range(4):
+        for b in val:
+            ops.weighted_avg(ref_t.base, [delta], w, ref_t.man, [ref_t.master], [ref_t.p16])
+            ref_t.loss_and_grad(b)
+            ops.multi_dot(ref_t.grad, [delta], ref_t.base, ref_t.master, ref_t.man, G)
+            w.add_(G, alpha=-0.05)
+    moved = float((w - 1).abs().max())
+    assert moved > 1e-6
+    assert float((ml.w - w).abs().max()) < 0.05 * moved + 1e-6
+    ml.final_average_shard(1)
+    want = torch.empty_like(ref_t.master)
+    ops.weighted_avg(ref_t.base, [delta], ml.w, ref_t.man, [want])
+    got = ex.win.local("base", torch.float32)[:tr.man.total]
+    assert float((got - want).abs().max()) < 1e-6
+    ex.win.check_errors()
+    ex.win.close()
