@@ -173,8 +173,10 @@ class DistributedMetaLearner:
     def step(self, k: int) -> None:
         """One reference meta-step (averaging_logic.py:499-528) on validation batch ``k``."""
         t, man = self.t, self.t.man
-        self.tick += 1
-        tick = self.tick
+        # the tick sequence belongs to the EXCHANGE (its flag words are monotonic): a second learner on the same windows continues it
+        tick = self.tick = (getattr(self.ex, "_meta_tick", 0) + 1) if self.ex is not None else self.tick + 1
+        if self.ex is not None:
+            self.ex._meta_tick = tick
         if self.peer:
             ex, win = self.ex, self.ex.win
             from .symm import F_G, F_GP, F_TB
