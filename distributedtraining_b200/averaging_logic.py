@@ -46,6 +46,24 @@ class Averager:
         self.last_pull_time = 0.0
         self.check_update_interval = 300
         self.round = 0
+        self.checkpoint_hook = None  # callable(averager, round): periodic --save_every
+
+    # -- durable state (the reference re-creates w every round and never saves it: averaging_logic.py:492) ------------------
+    def state_dict(self) -> Dict:
+        hf = self.hf_manager
+        return {"round": self.round, "weights": getattr(self, "weights", None), "consumed": dict(getattr(self, "_consumed", {})),
+                "miner_hotkeys": list(getattr(self, "miner_hotkeys", [])), "published_round": getattr(hf, "_published_round", 0),
+                "avg_round": getattr(self, "_avg_round", 0)}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.round = int(sd.get("round", 0))
+        if sd.get("weights") is not None and hasattr(self, "weights"):
+            self.weights = sd["weights"].to(self.model.master.device)
+        if hasattr(self, "_consumed"):
+            self._consumed.update(sd.get("consumed", {}))
+        self._avg_round = int(sd.get("avg_round", 0))
+        if self.hf_manager is not None:
+            self.hf_manager._published_round = max(getattr(self.hf_manager, "_published_round", 0), int(sd.get("published_round", 0)))
 
     # -- inputs -----------------------------------------------------------------------------------------------------
     def _repo_of(self, hotkey: str):
@@ -131,6 +149,8 @@ class Averager:
             self.save_model()
             self._adopt_as_base()
             self.push_to_hf_hub(commit_message="Updated model with new gradients")
+            if self.checkpoint_hook is not None:
+                self.checkpoint_hook(self, self.round)
             rounds += 1
             if max_rounds is not None and rounds >= max_rounds:
                 return
@@ -323,6 +343,8 @@ class ParameterizedAverager(DeltaAverager):
                 self.save_model()
                 self._adopt_as_base()
                 self.push_to_hf_hub(commit_message="Updated model with new gradients")
+                if self.checkpoint_hook is not None:
+                    self.checkpoint_hook(self, self.round)
                 idle_since = time.time()
             else:
                 logger.debug("No valid deltas this round")

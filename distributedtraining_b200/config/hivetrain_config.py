@@ -44,6 +44,7 @@ def add_b200_args(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--mixer", type=str, default="learned", choices=["learned", "uniform", "score", "genetic"])
     g.add_argument("--meta_epochs", type=int, default=7)
     g.add_argument("--meta_lr", type=float, default=0.01)
+    g.add_argument("--val_batch", type=int, default=8, help="co-located job: validation batch size of the learned mixer")
     g.add_argument("--meta_dropout", action="store_true", help="keep dropout on in the averager's meta-gradient passes (reference behaviour; default: deterministic)")
     g.add_argument("--roles", type=str, default="", help="e.g. 'miner:0-6,validator:7,averager:0'")
     g.add_argument("--backend", type=str, default="peer", choices=["peer", "nccl", "gloo", "disk"])
@@ -53,3 +54,8 @@ def add_b200_args(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--wall_clock", action="store_true", help="reference cadence: time-based send/poll intervals")
     g.add_argument("--inject", type=str, default="", help="fault injection 'nan|shape|stall|drop:rank[,..]'")
     g.add_argument("--metrics_jsonl", type=str, default="")
+    # real-text data path (reference: WikiText-103 train / test[:100]); unset = synthetic tokens of the same shape
+    g.add_argument("--data.train_file", type=str, default="", help="text file, one text per line (miner)")
+    g.add_argument("--data.val_file", type=str, default="", help="text file, one text per line (validator / averager: first 100 lines)")
+    g.add_argument("--data.tokenizer", type=str, default="byte", help="'byte' or an HF tokenizer directory")
+    g.add_argument("--flag_timeout", type=float, default=13.0, help="seconds before a device-side peer flag wait gives up")

@@ -44,6 +44,7 @@ class LocalSGDCoordinator:
         self.meta_log = meta_log
         self.timer = PhaseTimer(enabled=True)  # CUDA-event phase timers (read once, at the end of a bench)
         self.round = 0
+        self.round_base = 0  # rounds completed before a resume
         self.meta_steps_done = 0
         N, P = len(self.miners), len(trainer.man)
         dev = trainer.master.device
@@ -56,6 +57,22 @@ class LocalSGDCoordinator:
             self.w = self.meta.w
         else:
             self.w = torch.full((N, P), 1.0 / N, dtype=torch.float32, device=dev)  # softmax(ones) == 1/N
+
+    # -- durable state --------------------------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """``round_base + round`` rounds completed so far (the flag words of a restarted job begin at zero again, so the
+        live counter restarts while the total keeps counting), the mixing matrix and the meta-step counter."""
+        return {"rounds_total": self.round_base + self.round, "w": self.w.detach().clone(), "meta_steps_done": self.meta_steps_done}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.round_base = int(sd.get("rounds_total", 0))
+        self.meta_steps_done = int(sd.get("meta_steps_done", 0))
+        if sd.get("w") is not None and tuple(sd["w"].shape) == tuple(self.w.shape):
+            self.w.copy_(sd["w"].to(self.w.device))
+
+    @property
+    def rounds_total(self) -> int:
+        return self.round_base + self.round
 
     @property
     def learning(self) -> bool:

@@ -55,6 +55,27 @@ class ModelValidator:
         self.normalized_scores = {hk: 0.0 for hk in hotkeys}
         self.loss_scores = {hk: 0.0 for hk in hotkeys}
         self.losses: Dict[str, float] = {}
+        self.rounds_done = 0
+        self.checkpoint_hook = None  # callable(validator, round): periodic --save_every
+
+    # -- durable state (the reference keeps scores and the EMA in memory only: btt_connector.py:305-307) --------------------
+    def state_dict(self) -> Dict:
+        net = self.bittensor_network
+        ema = getattr(net, "base_scores", None)
+        return {"scores": dict(self.scores), "normalized_scores": dict(self.normalized_scores), "loss_scores": dict(self.loss_scores),
+                "losses": dict(self.losses), "base_loss": self.base_loss, "base_perplexity": self.base_perplexity,
+                "rounds_done": self.rounds_done, "score_ema": ema.clone() if isinstance(ema, torch.Tensor) else None}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.scores.update(sd.get("scores", {}))
+        self.normalized_scores.update(sd.get("normalized_scores", {}))
+        self.loss_scores.update(sd.get("loss_scores", {}))
+        self.losses.update(sd.get("losses", {}))
+        self.rounds_done = int(sd.get("rounds_done", 0))
+        ema, net = sd.get("score_ema"), self.bittensor_network
+        if ema is not None and net is not None and getattr(net, "base_scores", None) is not None \
+                and net.base_scores.numel() == ema.numel():
+            net.base_scores.copy_(ema)
 
     # -- delta application ------------------------------------------------------------------------------------------
     def update_model_weights(self, gradients, alpha: float = 5e-4) -> None:
@@ -168,6 +189,9 @@ class ModelValidator:
             if self.hf_manager is not None:
                 self.hf_manager.clear_hf_cache()
             rounds += 1
+            self.rounds_done += 1
+            if self.checkpoint_hook is not None:
+                self.checkpoint_hook(self, self.rounds_done)
             if self.max_rounds is not None and rounds >= self.max_rounds:
                 return
             time.sleep(max(0.0, self.interval - (time.time() - t0)))

@@ -10,7 +10,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from distributedtraining_b200.data import SyntheticTokens  # noqa: E402
+from distributedtraining_b200.data import SyntheticTokens, build_text_loader  # noqa: E402
 from distributedtraining_b200.models.trainer import Trainer  # noqa: E402
 from distributedtraining_b200.runtime import build_context  # noqa: E402
 from distributedtraining_b200.training_manager import DeltaLoop  # noqa: E402
@@ -25,8 +25,12 @@ def main(argv=None):
                       dropout=getattr(cfg, "dropout", None), dropout_seed=ctx.rank)
     resumed_round = maybe_resume(cfg, trainer, ctx.rank)
     # reference: WikiText-103 train split @ max_length 64, no shuffle (neurons/miner.py:54-106); offline: synthetic tokens
-    data_loader = SyntheticTokens(batch_size, cfg.seq_len, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1,
-                                  seed=ctx.rank)
+    if cfg.data.train_file:  # real text: per-item tokenisation to max_length ids, right-padded, no shuffle (reference :69-106)
+        data_loader = build_text_loader(cfg.data.train_file, cfg.data.tokenizer, trainer.cfg.vocab_size, batch_size, cfg.seq_len,
+                                        drop_last=True, repeat=True)
+    else:
+        data_loader = SyntheticTokens(batch_size, cfg.seq_len, trainer.cfg.vocab_size, pad_id=trainer.cfg.vocab_size - 1,
+                                      seed=ctx.rank)
     max_steps = cfg.rounds * cfg.local_steps if cfg.rounds else None
     loop = DeltaLoop(ctx.device, cfg.model, data_loader, send_interval=cfg.miner.send_interval, learning_rate=cfg.lr,
                      hf_manager=ctx.hf_manager, trainer=trainer, local_steps=None if cfg.wall_clock else cfg.local_steps,
