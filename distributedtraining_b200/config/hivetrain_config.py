@@ -58,4 +58,6 @@ def add_b200_args(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--data.train_file", type=str, default="", help="text file, one text per line (miner)")
     g.add_argument("--data.val_file", type=str, default="", help="text file, one text per line (validator / averager: first 100 lines)")
     g.add_argument("--data.tokenizer", type=str, default="byte", help="'byte' or an HF tokenizer directory")
+    g.add_argument("--validate_every", type=int, default=0, help="co-located job: all ranks score the deltas every N rounds (0 = off)")
+    g.add_argument("--eval_rows", type=int, default=52, help="rows per eval batch of the co-located validator")
     g.add_argument("--flag_timeout", type=float, default=13.0, help="seconds before a device-side peer flag wait gives up")

@@ -24,12 +24,16 @@ namespace dtb {
 // ------------------------------------------------------------------------------------------------------------------
 // AdamW
 // ------------------------------------------------------------------------------------------------------------------
-// hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, bias_corr1, bias_corr2
+// hyper (device, fp32[12]): lr, beta1, beta2, eps, weight_decay, grad_scale, bias_corr1, bias_corr2, fresh, -, -, -
+// fresh = 1 on the FIRST step after an optimizer (re-)creation: the moments are zero by definition, so the step kernel neither
+// reads them nor needs them cleared beforehand -- the reset the reference performs after every base pull
+// (hivetrain/training_manager.py:371-373) costs no memory traffic at all (1 GB less written per round, 1 GB less read per first step).
 __global__ void adam_prep_kernel(int* step, float* hyper) {
   const int t = *step + 1;
   *step = t;
   hyper[6] = 1.f - powf(hyper[1], float(t));
   hyper[7] = 1.f - powf(hyper[2], float(t));
+  hyper[8] = (t == 1) ? 1.f : 0.f;
 }
 
 template <int DELTA_MODE>  // 0: none, 1: fp32 delta, 2: bf16 delta
@@ -40,10 +44,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, 
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
   const float step_size = lr * sqrtf(hyper[7]) / hyper[6];
   const float decay = 1.f - lr * wd;
+  const bool fresh = hyper[8] != 0.f;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
     float4 g = reinterpret_cast<const float4*>(grad)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!fresh) {
+      mm = reinterpret_cast<float4*>(m)[i];
+      vv = reinterpret_cast<float4*>(v)[i];
+    }
     float4 p = reinterpret_cast<float4*>(master)[i];
     float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* pp = &p.x;
 #pragma unroll
@@ -359,14 +367,24 @@ __global__ void __launch_bounds__(256) shard_pull_reset_kernel(const __grid_cons
     const float* src = p.shard_src[owner];
     const size_t start = size_t(p.chunk_start[c]);
     const int len = p.chunk_len[c];
-    for (int v4 = threadIdx.x; v4 * 4 < len; v4 += blockDim.x) {
+    // a full chunk is 4096 elements = 1024 float4 = 4 per thread: all four (peer) loads are issued before the first store
+    const int n4 = len >> 2;
+    float4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v4 = threadIdx.x + k * 256;
+      if (v4 < n4) x[k] = *reinterpret_cast<const float4*>(src + start + size_t(v4) * 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v4 = threadIdx.x + k * 256;
+      if (v4 >= n4) continue;
       const size_t e = start + size_t(v4) * 4;
-      const float4 x = *reinterpret_cast<const float4*>(src + e);
-      *reinterpret_cast<float4*>(p.base_out + e) = x;
-      *reinterpret_cast<float4*>(p.master + e) = x;
+      if (p.base_out) *reinterpret_cast<float4*>(p.base_out + e) = x[k];
+      *reinterpret_cast<float4*>(p.master + e) = x[k];
       if (p.p16) {
         uint2 o;
-        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x[k].x, x[k].y), hi = __floats2bfloat162_rn(x[k].z, x[k].w);
         o.x = *reinterpret_cast<uint32_t*>(&lo);
         o.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(p.p16 + e) = o;

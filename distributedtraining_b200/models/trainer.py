@@ -177,7 +177,7 @@ class Trainer:
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         self.master.copy_(sd["master"]); self.base.copy_(sd["base"]); self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
-        self.opt.step.copy_(sd["step"]); self.opt.hyper.copy_(sd["hyper"])
+        self.opt.step.copy_(sd["step"]); self.opt.hyper[:sd["hyper"].numel()].copy_(sd["hyper"])
         self.opt.host_step = int(sd["step"])
         self.opt.host["lr"] = float(sd["hyper"][0])
         if self.is_cuda:

@@ -287,8 +287,11 @@ class TransformerEngine:
     """Static-buffer forward/backward.  ``params`` is the compute-dtype arena (bf16 on GPU), ``grads`` the fp32 arena."""
 
     def __init__(self, cfg: ModelConfig, manifest: Manifest, params: torch.Tensor, grads: Optional[torch.Tensor],
-                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False, seed: int = 0):
+                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False, seed: int = 0, eval_only: bool = False):
         self.cfg, self.man = cfg, manifest
+        # eval_only: forward passes only -> ONE set of per-layer activation buffers shared by all layers (the validator scores
+        # 51 200 tokens per miner: per-layer buffers for GPT-2-medium would be 40 GB, shared ones 1.7 GB)
+        self.eval_only = bool(eval_only) and grads is None
         assert cfg.dropout == 0.0 or cfg.family == "gpt2", "dropout sites are defined for the GPT-2 family"
         self.drop_p = float(cfg.dropout)
         self.rng = ops.DropoutRng(params.device, seed=0x5EED + seed)
@@ -308,20 +311,30 @@ class TransformerEngine:
         mk = lambda *shape, dtype=None: torch.empty(*shape, dtype=dtype or self.cdtype, device=self.dev)
         L = cfg.n_layer
         glu = cfg.family == "llama"
-        self.xs = [mk(M, d) for _ in range(L + 1)]  # residual stream at layer boundaries
-        self.xmid = [mk(M, d) for _ in range(L)]
-        self.h1 = [mk(M, d) for _ in range(L)]
-        self.h2 = [mk(M, d) for _ in range(L)]
-        self.qkv = [mk(M, cfg.qkv_dim) for _ in range(L)]
-        self.att = [mk(M, cfg.n_head * cfg.head_dim) for _ in range(L)]
-        self.lse = [mk(batch, cfg.n_head, seq, dtype=torch.float32) for _ in range(L)]
-        self.u = [mk(M, 2 * Fd if glu else Fd) for _ in range(L)]  # pre-activation
-        self.act = [mk(M, Fd) for _ in range(L)]
         f32 = torch.float32
-        self.mean1 = [mk(M, dtype=f32) for _ in range(L)]
-        self.rstd1 = [mk(M, dtype=f32) for _ in range(L)]
-        self.mean2 = [mk(M, dtype=f32) for _ in range(L)]
-        self.rstd2 = [mk(M, dtype=f32) for _ in range(L)]
+
+        def per_layer(n, *shape, dtype=None):  # n buffers, or (eval_only) one buffer aliased n times
+            if self.eval_only:
+                one = mk(*shape, dtype=dtype)
+                return [one] * n
+            return [mk(*shape, dtype=dtype) for _ in range(n)]
+        if self.eval_only:
+            a, b = mk(M, d), mk(M, d)
+            self.xs = [a if l % 2 == 0 else b for l in range(L + 1)]  # residual stream ping-pongs between two buffers
+        else:
+            self.xs = [mk(M, d) for _ in range(L + 1)]  # residual stream at layer boundaries
+        self.xmid = per_layer(L, M, d)
+        self.h1 = per_layer(L, M, d)
+        self.h2 = per_layer(L, M, d)
+        self.qkv = per_layer(L, M, cfg.qkv_dim)
+        self.att = per_layer(L, M, cfg.n_head * cfg.head_dim)
+        self.lse = per_layer(L, batch, cfg.n_head, seq, dtype=f32)
+        self.u = per_layer(L, M, 2 * Fd if glu else Fd)  # pre-activation
+        self.act = per_layer(L, M, Fd)
+        self.mean1 = per_layer(L, M, dtype=f32)
+        self.rstd1 = per_layer(L, M, dtype=f32)
+        self.mean2 = per_layer(L, M, dtype=f32)
+        self.rstd2 = per_layer(L, M, dtype=f32)
         self.xf = mk(M, d)
         self.meanf, self.rstdf = mk(M, dtype=f32), mk(M, dtype=f32)
         self.lm_chunk = min(lm_chunk, M)
@@ -330,16 +343,17 @@ class TransformerEngine:
         self.losses = mk(M, dtype=f32)
         self.loss = torch.zeros((), dtype=f32, device=self.dev)
         # backward scratch
-        self.dx = mk(M, d)
-        self.dx2 = mk(M, d)
-        self.dxf = mk(M, d)
-        if self.drop_p > 0.0 and grads is not None:
-            self.dxm, self.dxm2 = mk(M, d), mk(M, d)  # dropout-masked copies of the residual-stream gradient
-        self.dh = mk(M, d)
-        self.dqkv = mk(M, cfg.qkv_dim)
-        self.datt = mk(M, cfg.n_head * cfg.head_dim)
-        self.du = mk(M, 2 * Fd if glu else Fd)
-        self.dact = mk(M, Fd) if glu else None
+        if not self.eval_only:
+            self.dx = mk(M, d)
+            self.dx2 = mk(M, d)
+            self.dxf = mk(M, d)
+            if self.drop_p > 0.0 and grads is not None:
+                self.dxm, self.dxm2 = mk(M, d), mk(M, d)  # dropout-masked copies of the residual-stream gradient
+            self.dh = mk(M, d)
+            self.dqkv = mk(M, cfg.qkv_dim)
+            self.datt = mk(M, cfg.n_head * cfg.head_dim)
+            self.du = mk(M, 2 * Fd if glu else Fd)
+            self.dact = mk(M, Fd) if glu else None
         # ---- optional fp8 (e4m3) forward GEMMs with delayed per-tensor scaling (BASELINE.json config 4: "fp8 miners") ----
         # forward GEMM operands are quantised (weights once per step, activations by a one-pass quantise kernel that also
         # collects the amax for the NEXT step); backward GEMMs stay bf16.  All scales live in two device vectors.

@@ -326,8 +326,9 @@ class AdamState:
 
     def __init__(self, device, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, grad_scale=1.0):
         self.device = torch.device(device)
-        self.hyper = torch.tensor([lr, beta1, beta2, eps, weight_decay, grad_scale, 1.0, 1.0], dtype=torch.float32,
-                                  device=device)
+        # [8] = "fresh": first step after (re-)creation -> the moments are implicitly zero (see csrc/optim_avg.cu adam_prep)
+        self.hyper = torch.tensor([lr, beta1, beta2, eps, weight_decay, grad_scale, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0],
+                                  dtype=torch.float32, device=device)
         self.step = torch.zeros((), dtype=torch.int32, device=device)
         self.host = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)
         self.host_step = 0
@@ -347,6 +348,9 @@ def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None)
     if not use_kernels(master):
         h = state.host
         state.step += 1
+        if state.host_step == 1:  # first step after (re-)creation: moments are zero by definition (lazy optimizer reset)
+            m.zero_()
+            v.zero_()
         ref.adamw_step(master, p16, grad, m, v, lr=h["lr"], beta1=h["beta1"], beta2=h["beta2"], eps=h["eps"],
                        weight_decay=h["weight_decay"], step=state.host_step, grad_scale=h["grad_scale"])
         if delta is not None:

@@ -30,7 +30,8 @@ class LocalSGDCoordinator:
     def __init__(self, trainer, exchange=None, miners: Optional[List[int]] = None, averager_rank: int = 0,
                  mixer: str = "learned", meta_steps: int = 0, meta_lr: float = 0.01, val_batches: Optional[list] = None,
                  post_pull_lr: Optional[float] = 5e-5, reset_optimizer: bool = True, meta_epochs: int = 0,
-                 meta_mode: str = "auto", meta_dropout: bool = False, reset_w: bool = True, meta_log=None):
+                 meta_mode: str = "auto", meta_dropout: bool = False, reset_w: bool = True, meta_log=None,
+                 validator=None, validate_every: int = 0):
         self.trainer = trainer
         self.ex = exchange
         self.rank = getattr(exchange, "rank", 0)
@@ -42,6 +43,9 @@ class LocalSGDCoordinator:
         self.post_pull_lr, self.reset_optimizer = post_pull_lr, reset_optimizer
         self.reset_w = reset_w  # reference: w is rebuilt (1/N) at every averaging round (averaging_logic.py:492)
         self.meta_log = meta_log
+        # optional co-located validator (validation_logic.CollectiveDeltaValidator): scores the round's deltas against the
+        # OLD base, i.e. after the publish and before the averaging replaces theta_base
+        self.validator, self.validate_every = validator, int(validate_every)
         self.timer = PhaseTimer(enabled=True)  # CUDA-event phase timers (read once, at the end of a bench)
         self.round = 0
         self.round_base = 0  # rounds completed before a resume
@@ -93,6 +97,11 @@ class LocalSGDCoordinator:
             ex = self.ex
             with self.timer.phase("delta_emit"):
                 ex.publish_delta(t, r)
+            if self.validator is not None and self.validate_every > 0 and self.rounds_total % self.validate_every == 0:
+                with self.timer.phase("validate"):
+                    ex.win.wait(ex.F_DELTA, r, self.miners)  # every miner's delta of this round has landed
+                    torch.cuda.current_stream().synchronize()  # the scorer reads the flag page on the host (once per round)
+                    self.validator.validate_and_score(round=r)
             if self.learning:
                 # learned mixer on ALL ranks: delta all-to-all by pull once, then meta_steps sharded SGD steps on w
                 with self.timer.phase("meta_prepare"):
@@ -108,8 +117,10 @@ class LocalSGDCoordinator:
                     active = ex.prepare_round(r, self.miners, self.w, init_w=True)
                     per = ex.reduce_scatter_average(t.base, self.w, r, self.miners, active=active)
             # all-gather by pull fused with the base / optimizer reset (no pushes: P2P stores are the slow direction)
+            # the Adam moments are NOT rewritten: opt.reset() puts the step counter at 0 and the first step kernel treats them as
+            # zero (the "fresh" flag) -- the optimizer re-creation of the reference without 1 GB of stores per round
             with self.timer.phase("broadcast_reset"):
-                ex.all_gather_reset(t, per, reset_moments=self.reset_optimizer)
+                ex.all_gather_reset(t, per, reset_moments=False)
             if self.reset_optimizer:
                 t.opt.reset()
             if self.post_pull_lr is not None:

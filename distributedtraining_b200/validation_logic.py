@@ -253,6 +253,164 @@ class DeltaValidator(ModelValidator):
             super().restore_base()
 
 
+class EvalModel:
+    """Forward-only scoring model: one bf16 parameter arena + an eval-only engine (activation buffers shared by all layers)
+    + one CUDA graph per batch shape.  ``load()`` materialises ``theta_base (+ delta_i)`` with ONE fused kernel that reads
+    the delta straight from the miner's peer window; nothing else of the model state is touched (theta_base is never mutated:
+    the reference's deepcopy / load_state_dict pair per miner, validation_logic.py:123,139, has no counterpart)."""
+
+    def __init__(self, cfg, man, device, rows: int, seq: int, lm_chunk: int = 8192):
+        from .models.transformer import TransformerEngine
+        self.cfg, self.man, self.device = cfg, man, torch.device(device)
+        self.is_cuda = self.device.type == "cuda"
+        self.p16 = torch.empty(man.total, dtype=torch.bfloat16 if self.is_cuda else torch.float32, device=self.device)
+        self.engine = TransformerEngine(cfg, man, self.p16, None, rows, seq, lm_chunk=lm_chunk, eval_only=True)
+        self._graphs = {}
+        self._acc = torch.zeros((), dtype=torch.float64, device=self.device)
+        self._ones = torch.ones(1, len(man), dtype=torch.float32, device=self.device)
+
+    def load(self, base: torch.Tensor, delta=None, dscale=None, mode: int = 0) -> None:
+        """p16 = compute-dtype(base + delta); ``delta``: tensor or raw peer address (typed by ``mode``: 0 fp32, 1 bf16, 2 fp8)."""
+        if delta is None:
+            if self.is_cuda:
+                ops.cast_copy(base, self.p16)
+            else:
+                self.p16.copy_(base)
+            return
+        if self.is_cuda:
+            ops.weighted_avg(base, [delta], self._ones, self.man, [None], [self.p16], dscales=[dscale] if dscale is not None else None,
+                             mode=mode, unit_base=True)
+        else:
+            self.p16.copy_(base + delta.to(base.device, torch.float32))
+
+    def _forward(self) -> None:
+        e = self.engine
+        if not self.is_cuda:
+            e.forward_loss()
+            return
+        key = e.n_rows  # the CE normaliser is a kernel argument: one graph per row count
+        g = self._graphs.get(key)
+        if g is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                e.forward_loss()
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e.forward_loss()
+            self._graphs[key] = g
+        g.replay()
+
+    @torch.no_grad()
+    def mean_loss(self, batches) -> torch.Tensor:
+        """Row-weighted mean of the per-batch mean CE (reference evaluate_model, :78-97) as a DEVICE scalar (no host sync)."""
+        self._acc.zero_()
+        n = 0
+        for b in batches:
+            self.engine.set_batch(b)
+            self._forward()
+            self._acc += self.engine.loss.double() * self.engine.n_rows
+            n += self.engine.n_rows
+        return self._acc / max(n, 1)
+
+
+def rebatch(batches, rows: int):
+    """Concatenate dict batches into batches of ``rows`` sequences.  Every row carries the same number of targets (PAD is
+    not masked in the labels), so the row-weighted mean of per-batch means is the same number for any batch size -- the
+    validator may evaluate 100 texts in one or two big GEMM-friendly batches instead of 13 small ones."""
+    keys = [k for k in batches[0] if isinstance(batches[0][k], torch.Tensor)]
+    cat = {k: torch.cat([b[k] for b in batches], dim=0) for k in keys}
+    n = cat["input_ids"].shape[0]
+    return [{k: v[i:i + rows] for k, v in cat.items()} for i in range(0, n, rows)]
+
+
+class CollectiveDeltaValidator(DeltaValidator):
+    """Co-located validator: ALL ranks of the box score the miners' deltas together (the reference scores them serially on
+    one machine, validation_logic.py:126-183).
+
+    Jobs = the N miners + the base model; job k runs on rank ``k % world``: fused delta-apply straight from the miner's peer
+    window (one NVLink read of the delta) -> graph-captured eval forward over the validation set in large batches -> one
+    device scalar.  The NaN / missing-miner verdicts come from the publish flags (no pass over the delta, no host sync per
+    miner); the loss table is combined with one tiny all-reduce, after which the score maths of the reference (:136-187)
+    runs unchanged on every rank and the validator rank commits the weights.  Every rank calls :meth:`validate_and_score`.
+    """
+
+    def __init__(self, device, model, data_loader, bittensor_network, exchange, miner_ranks, validator_rank: int = 0,
+                 eval_rows: Optional[int] = None, group=None, **kw):
+        self.exchange = exchange
+        self.miner_ranks = list(miner_ranks)
+        self.validator_rank = validator_rank
+        self.group = group
+        import torch.distributed as dist
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        batches = list(data_loader)
+        if eval_rows:
+            batches = rebatch(batches, eval_rows)
+        rows = max(int(b["input_ids"].shape[0]) for b in batches)
+        seq = int(batches[0]["input_ids"].shape[1])
+        self.batches = [{k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in b.items()} for b in batches]
+        self.evalm = EvalModel(model.cfg, model.man, device, rows, seq)
+        self.round = 0
+        super().__init__(device, model, None, self.batches, bittensor_network, kw.pop("hf_manager", None), **kw)
+
+    def evaluate_model(self, metric: str = "loss") -> Tuple[float, float]:
+        """Loss / perplexity of the CURRENT base (constructor, base refresh)."""
+        self.evalm.load(self.model.base)
+        avg = float(self.evalm.mean_loss(self.batches))
+        return avg, math.exp(min(avg, 50.0))
+
+    def _miner_ok(self, flags, src: int, round: int) -> bool:
+        ex = self.exchange
+        return int(flags[ex.F_DELTA + src]) >= round and int(flags[ex.F_BAD + src]) != round
+
+    def validate_and_score(self, round: Optional[int] = None) -> Dict[str, float]:
+        import torch.distributed as dist
+        ex, net = self.exchange, self.bittensor_network
+        self.round = round if round is not None else self.round + 1
+        r = self.round
+        hot = list(net.metagraph.hotkeys)
+        jobs = list(self.miner_ranks) + [-1]            # -1 = the base model
+        table = torch.zeros(len(jobs), dtype=torch.float64, device=self.evalm.device)
+        flags = ex.win.flags().tolist() if hasattr(ex, "win") else None  # ONE host read of the local flag page per round
+        mode = {"fp32": 0, "bf16": 1, "fp8": 2}.get(getattr(ex, "delta_dtype_name", "fp32"), 0)
+        valid = []
+        for k, src in enumerate(jobs):
+            ok = src < 0 or flags is None or self._miner_ok(flags, src, r)
+            valid.append(ok)
+            if not ok or k % self.world != self.rank:
+                continue
+            if src < 0:
+                self.evalm.load(self.model.base)
+            else:
+                d, s = ex._delta_ptrs(r, [src])
+                self.evalm.load(self.model.base, d[0], s[0] if s else None, mode)
+            table[k] = self.evalm.mean_loss(self.batches)
+        if self.world > 1:
+            dist.all_reduce(table, group=self.group)
+        losses = table.tolist()                         # the round's single device->host read of results
+        self.base_loss = losses[-1]
+        self.base_perplexity = math.exp(min(self.base_loss, 50.0))
+        for k, src in enumerate(jobs[:-1]):
+            hk = f"rank{src}" if f"rank{src}" in hot else (hot[src] if src < len(hot) else str(src))
+            if valid[k]:
+                loss = losses[k]
+                ppl = math.exp(min(loss, 50.0))
+                ls, ps = max(0.0, self.base_loss - loss), max(0.0, self.base_perplexity - ppl)
+            else:
+                loss, ppl, ls, ps = float("nan"), float("nan"), 0.0, 0.0
+            self.losses[hk], self.loss_scores[hk], self.scores[hk] = loss, ls, ps
+            net.metrics_data[hk] = {"loss": loss if loss == loss else 1e9}
+            if self.rank == self.validator_rank:
+                self.metrics.log(hotkey=hk, loss=loss, perplexity=ppl, loss_score=ls, perplexity_score=ps)
+        total = sum(self.scores.values())
+        self.normalized_scores = {hk: (max(0.0, sc / total) if total > 0 else 0.0) for hk, sc in self.scores.items()}
+        if self.rank == self.validator_rank and net.should_set_weights():
+            net.set_weights(self.normalized_scores)
+        return self.normalized_scores
+
+
 class LocalValidator(ModelValidator):
     """Deltas come from a local directory tree ``<repo>/gradients.pt`` (reference :206-248)."""
 

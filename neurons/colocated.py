@@ -53,12 +53,18 @@ def main(argv=None):
         n_val = EVAL_TEXTS if not cfg.model.endswith("tiny") else 2 * vb
         vs = SyntheticTokens(n_val, vseq, V, pad_id=V - 1, seed=7, pool=1).pool[0]
         val = [{k: v[i:i + vb] for k, v in vs.items()} for i in range(0, n_val, vb)]
+    validator = None
+    if cfg.validate_every > 0 and isinstance(ex, PeerExchange):
+        from distributedtraining_b200.validation_logic import CollectiveDeltaValidator
+        validator = CollectiveDeltaValidator(ctx.device, trainer, val, ctx.network, ex, list(range(ctx.world)),
+                                             validator_rank=(ctx.roles.get("validator") or [0])[0], eval_rows=cfg.eval_rows or None,
+                                             metrics=ctx.metrics)
     learned = cfg.mixer == "learned" and cfg.meta_epochs > 0
     coord = LocalSGDCoordinator(trainer, ex, mixer="learned" if learned else "uniform", meta_epochs=cfg.meta_epochs if learned else 0,
                                 meta_lr=cfg.meta_lr, val_batches=val, post_pull_lr=cfg.post_pull_lr,
                                 reset_optimizer=not cfg.no_reset_optimizer, meta_dropout=bool(cfg.meta_dropout),
                                 meta_log=(lambda k, loss, wm: ctx.metrics.log(meta_pass=k, loss_averaged=loss, w_mean=wm))
-                                if ctx.rank == 0 else None)
+                                if ctx.rank == 0 else None, validator=validator, validate_every=cfg.validate_every)
     if getattr(trainer, "_resume_blob", None):
         coord.load_state_dict(trainer._resume_blob["extra"].get("coordinator", {}))
     ckpt = PeriodicCheckpointer(cfg, trainer, ctx.rank, "colocated")

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--eval-batches", type=int, default=13)   # 100 texts / batch 8 (reference neurons/validator.py:49,98)
     ap.add_argument("--eval-batch", type=int, default=8)
     ap.add_argument("--eval-seq", type=int, default=512)
+    ap.add_argument("--eval-rows", type=int, default=52, help="rows per eval batch of the collective validator (100 texts -> 2 batches)")
     a = ap.parse_args()
     rank, world, dev = init_distributed("nccl")
     vrank = world - 1
@@ -48,9 +49,44 @@ def main():
             mtr = tr
         for i in range(a.miner_steps):
             mtr.step(data.pool[i % 4]["input_ids"])
-        ex.publish_delta(mtr, 1, dst_ranks=[vrank])
+        ex.publish_delta(mtr, 1)  # to every rank: all ranks of the box score deltas together in the collective mode
     barrier_sync(dev)
     out = None
+    # ---- collective mode: N miners + the base = N+1 jobs spread over ALL ranks, large eval batches, CUDA-graph forward ----
+    from distributedtraining_b200.validation_logic import CollectiveDeltaValidator
+    cfg0 = Configurator.combine_configs([])
+    cfg0.wallet.hotkey = f"rank{rank}"
+    cfg0.neuron.epoch_length = 0
+    BittensorNetwork.initialize(cfg0, ignore_regs=True, ledger=MemoryLedger(), hotkeys=[f"rank{r}" for r in range(world)])
+    vloader = list(SyntheticTokens(a.eval_batch, a.eval_seq, V, seed=4242, device=str(dev), pool=a.eval_batches, steps=a.eval_batches))
+    cval = CollectiveDeltaValidator(dev, tr, vloader, BittensorNetwork, ex, miners, validator_rank=vrank, eval_rows=a.eval_rows)
+    coll = {}
+    for rep in range(3):
+        barrier_sync(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cval.validate_and_score(round=1)
+        e1.record()
+        torch.cuda.synchronize()
+        from distributedtraining_b200.parallel.launch import max_over_ranks
+        ms = max_over_ranks(e0.elapsed_time(e1), dev)
+        coll = {"ms_per_miner": ms / len(miners), "ms_round": ms, "losses": [cval.losses[f"rank{r}"] for r in miners],
+                "base_loss": cval.base_loss, "scores": [cval.normalized_scores[f"rank{r}"] for r in miners],
+                "eval_rows_per_batch": a.eval_rows, "jobs_per_rank": -(-(len(miners) + 1) // world)}
+    # the same large-batch graph-captured scoring on the validator rank ALONE (no help from the other ranks)
+    solo = {}
+    if is_val and world > 1:
+        sv = CollectiveDeltaValidator(dev, tr, vloader, BittensorNetwork, ex, miners, validator_rank=vrank, eval_rows=a.eval_rows)
+        sv.world, sv.rank = 1, 0
+        for rep in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sv.validate_and_score(round=1)
+            e1.record()
+            torch.cuda.synchronize()
+            solo = {"ms_per_miner": e0.elapsed_time(e1) / len(miners), "losses": [sv.losses[f"rank{r}"] for r in miners]}
+    barrier_sync(dev)
     if is_val:
         ex.win.wait(ex.F_DELTA, 1, miners)
         torch.cuda.synchronize()
@@ -77,7 +113,8 @@ def main():
             res[mode] = {"ms_per_miner": e0.elapsed_time(e1) / len(miners), "losses": [val.losses[h] for h in hot],
                          "base_loss": val.base_loss, "scores": [val.normalized_scores[h] for h in hot]}
         out = {"model": a.model, "world": world, "miners": len(miners), "eval_tokens_per_miner": a.eval_batches * B * T,
-               "delta_bytes_bf16": tr.man.total * 2, **res}
+               "delta_bytes_bf16": tr.man.total * 2, **res, "collective_all_ranks": coll, "large_batch_graph_one_rank": solo}
+        out["max_loss_diff_collective_vs_applied"] = max(abs(x - y) for x, y in zip(coll["losses"], res["applied"]["losses"]))
     # ---- NCCL-style baseline: broadcast each delta to the validator, torch add + cast, eval ----
     if world > 1:
         n = tr.man.total
