@@ -37,6 +37,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct AttnParams {
   CUtensorMap tmap_qkv;  // [M, qkv_dim], box 64 x 128
   CUtensorMap tmap_do;   // [M, H*64],   box 64 x 128 (backward)
+  CUtensorMap tmap_o;    // [M, H*64],   box 64 x 128 (backward, single-block kernel: O tile for D = rowsum(dO * O))
   CUtensorMap tmap_out;  // forward: out [M, H*64]; backward: dqkv [M, qkv_dim]; box 64 x 128 (single-block kernels store by TMA)
   const __nv_bfloat16* o;
   const __nv_bfloat16* dout;
@@ -354,6 +355,30 @@ DTB_DEVICE void load_row_stats(const AttnParams& p, int row_tok, int h, float& D
         Drow += fx.x * fy.x + fx.y * fy.y;
       }
     }
+    const int b_ = row_tok / p.T, t = row_tok % p.T;
+    lse_l2 = p.lse[(size_t(b_) * p.H + h) * p.T + t] * kLog2e;
+  }
+}
+
+// Same statistics from the TMA-loaded dO / O tiles in shared memory (128B-swizzled [128 x 64] bf16): replaces 16 row-strided
+// LDG.128 per thread (17 % of the single-block kernel's stall samples sat on their first use) with conflict-free LDS.
+DTB_DEVICE void row_stats_smem(const AttnParams& p, const uint8_t* sDO, const uint8_t* sO, int row, int row_tok, int h, float& Drow,
+                               float& lse_l2) {
+  Drow = 0.f;
+  lse_l2 = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+    const uint4 x = *reinterpret_cast<const uint4*>(sDO + off), y = *reinterpret_cast<const uint4*>(sO + off);
+    const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&x);
+    const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fx = __bfloat1622float2(xh[k]), fy = __bfloat1622float2(yh[k]);
+      Drow += fx.x * fy.x + fx.y * fy.y;
+    }
+  }
+  if (row_tok < p.M) {
     const int b_ = row_tok / p.T, t = row_tok % p.T;
     lse_l2 = p.lse[(size_t(b_) * p.H + h) * p.T + t] * kLog2e;
   }
@@ -849,11 +874,12 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   constexpr uint32_t idesc_q = make_idesc(kFmtBF16, kFmtBF16, false, true, 128, 64);
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(&bars[0], 4 * kTile);
+      mbar_expect_tx(&bars[0], 5 * kTile);
       tma_load_2d(sQ, &p.tmap_qkv, &bars[0], colQ, q0);
       tma_load_2d(sK, &p.tmap_qkv, &bars[0], colK, q0);
       tma_load_2d(sV, &p.tmap_qkv, &bars[0], colV, q0);
       tma_load_2d(sDO, &p.tmap_do, &bars[0], colQ, q0);
+      tma_load_2d(sDS, &p.tmap_o, &bars[0], colQ, q0);  // O tile parks in the (still dead) dS region until D is formed
     }
     mbar_wait(&bars[0], 0);
     tc_fence_after();
@@ -868,7 +894,9 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
     }
   }
   float Drow, lse_l2;
-  load_row_stats(p, row_tok, h, Drow, lse_l2);
+  if (warp != 0) mbar_wait(&bars[0], 0);  // (warp 0 passed it before issuing the MMAs) the dO / O tiles have landed
+  // each thread reads ITS row of the O tile here and overwrites only that same row of dS later: no barrier needed in between
+  row_stats_smem(p, sDO, sDS, tid, row_tok, h, Drow, lse_l2);
   const int c_lo = (row_tok / p.T) * p.T - q0, c_hi = row_last_key(p, row_tok) - q0;
   mbar_wait(&bars[1], 0);
   tc_fence_after();
@@ -1001,6 +1029,7 @@ extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* 
   const int M = B * T;
   if (make_tmap_2d(&p.tmap_qkv, qkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   if (make_tmap_2d(&p.tmap_do, dout, 2, uint64_t(H) * kHd, M, ld_o, 64, kBlk)) return 11;
+  if (make_tmap_2d(&p.tmap_o, o, 2, uint64_t(H) * kHd, M, ld_o, 64, kBlk)) return 11;
   if (make_tmap_2d(&p.tmap_out, dqkv, 2, uint64_t(H + 2 * Hkv) * kHd, M, ld_qkv, 64, kBlk)) return 11;
   p.o = (const __nv_bfloat16*)o; p.dout = (const __nv_bfloat16*)dout; p.out = (__nv_bfloat16*)dqkv;
   p.lse = const_cast<float*>(lse); p.M = M; p.T = T; p.H = H; p.Hkv = Hkv; p.ld_out = ld_qkv; p.ld_o = ld_o; p.scale = scale;
