@@ -11,6 +11,7 @@ This is the in-box replacement of the reference's tensor plane: ``torch.save`` -
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -71,13 +72,22 @@ class SymmetricWindow:
             self.regions[name] = Region(name, off, nbytes)
             off += nbytes
         self.nbytes = off
+        self.peer_ptrs: List[int] = [0] * self.world
+        self.p2p = True
+        self.mc_ptr = 0  # multicast (NVLS) address of the windows; 0 = this window cannot be addressed through the switch
+        self.backing = "ipc"
+        want = os.environ.get("DTB200_SYMM", "vmm")
+        if want == "vmm" and self._init_vmm(L, group):
+            self.backing = "vmm"
+            self._local = tensor_from_ptr(self.local_ptr, self.nbytes, self.device)
+            self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._epoch = 0
+            return
         p = ctypes.c_void_p()
         _lib.check(L.dtb_symm_alloc(ctypes.c_size_t(self.nbytes), ctypes.byref(p)), "dtb_symm_alloc")
         self.local_ptr = p.value
         self._local = tensor_from_ptr(self.local_ptr, self.nbytes, self.device)
-        self.peer_ptrs: List[int] = [0] * self.world
         self.peer_ptrs[self.rank] = self.local_ptr
-        self.p2p = True
         if self.world > 1:
             h = ctypes.create_string_buffer(64)
             _lib.check(L.dtb_ipc_get_handle(ctypes.c_void_p(self.local_ptr), h), "ipc_get_handle")
@@ -96,6 +106,105 @@ class SymmetricWindow:
             dist.barrier(group=group)
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._epoch = 0
+
+    # -- VMM + NVLS multicast backing (csrc/symm_runtime.cu) ----------------------------------------------------------
+    def _init_vmm(self, L, group) -> bool:
+        """cuMemCreate window -> POSIX fd -> every peer maps it (unicast, NVLink P2P) and all windows are bound to ONE
+        multicast object (``multimem.*`` through the NVSwitch).  The fds travel over unix sockets (SCM_RIGHTS).  Any failure
+        (old driver, no fabric, sandboxed /tmp) makes every rank fall back to the cudaMalloc + CUDA-IPC backing."""
+        import socket
+        import tempfile
+        import uuid
+        dev = self.device.index
+        if not hasattr(L, "dtb_vmm_granularity"):
+            return False
+        L.dtb_vmm_granularity.restype = ctypes.c_size_t
+        gran = int(L.dtb_vmm_granularity(dev, self.world))
+        ok = gran > 0
+        size = (self.nbytes + gran - 1) // gran * gran if ok else 0
+        handle, ptr, fd = ctypes.c_ulonglong(0), ctypes.c_void_p(), ctypes.c_int(-1)
+        if ok:
+            ok = L.dtb_vmm_alloc(ctypes.c_size_t(size), ctypes.c_size_t(gran), dev, ctypes.byref(handle), ctypes.byref(ptr),
+                                 ctypes.byref(fd)) == 0
+
+        def all_ok(flag: bool) -> bool:
+            if self.world == 1:
+                return flag
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item())
+        if not all_ok(ok):
+            return False
+        self.local_ptr = ptr.value
+        self.peer_ptrs[self.rank] = self.local_ptr
+        self.nbytes_mapped = size
+        if self.world == 1:
+            return True
+        # ---- rank 0 creates the multicast object; fds are handed over rank by rank ----
+        mc, mc_fd = ctypes.c_ulonglong(0), ctypes.c_int(-1)
+        want_mc = bool(L.dtb_mc_supported(dev)) and os.environ.get("DTB200_NO_MULTICAST", "0") != "1"
+        if self.rank == 0 and want_mc:
+            want_mc = L.dtb_mc_create(self.world, ctypes.c_size_t(size), ctypes.byref(mc), ctypes.byref(mc_fd)) == 0
+        want_mc = all_ok(want_mc)
+        token = [uuid.uuid4().hex if self.rank == 0 else None]
+        dist.broadcast_object_list(token, src=0, group=group)
+        path = lambda r: os.path.join(tempfile.gettempdir(), f"dtb200_{token[0]}_{r}.sock")
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(path(self.rank))
+        srv.listen(self.world)
+        dist.barrier(group=group)
+        peer_fds = {}
+        try:
+            for p in range(self.world):
+                if p == self.rank:
+                    for _ in range(self.world - 1):  # hand my window fd (and, from rank 0, the multicast fd) to every peer
+                        c, _a = srv.accept()
+                        fds = [fd.value] + ([mc_fd.value] if (self.rank == 0 and want_mc) else [])
+                        socket.send_fds(c, [b"w"], fds)
+                        c.close()
+                else:
+                    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                    c.connect(path(p))
+                    _m, fds, _f, _ad = socket.recv_fds(c, 16, 2)
+                    c.close()
+                    peer_fds[p] = list(fds)
+        finally:
+            srv.close()
+            try:
+                os.unlink(path(self.rank))
+            except OSError:
+                pass
+        good = True
+        for p, fds in peer_fds.items():
+            q = ctypes.c_void_p()
+            rc = L.dtb_vmm_import(fds[0], ctypes.c_size_t(size), ctypes.c_size_t(gran), dev, ctypes.byref(q))
+            good = good and rc == 0
+            self.peer_ptrs[p] = q.value or 0
+            os.close(fds[0])
+            if p == 0 and want_mc and len(fds) > 1:
+                good_mc = L.dtb_mc_import(fds[1], ctypes.byref(mc)) == 0
+                os.close(fds[1])
+                want_mc = want_mc and good_mc
+        if not all_ok(good):
+            raise RuntimeError("VMM peer mapping failed on some rank (set DTB200_SYMM=ipc to use CUDA IPC windows)")
+        os.close(fd.value)
+        if self.rank == 0 and mc_fd.value >= 0:
+            os.close(mc_fd.value)
+        want_mc = all_ok(want_mc)
+        if want_mc:
+            want_mc = all_ok(L.dtb_mc_add_device(mc, dev) == 0)
+        if want_mc:  # every device has been added (the all-reduce above is the barrier the driver asks for): bind + map
+            q = ctypes.c_void_p()
+            rc = L.dtb_mc_bind_map(mc, handle, ctypes.c_size_t(size), ctypes.c_size_t(gran), dev, ctypes.byref(q))
+            if all_ok(rc == 0):
+                self.mc_ptr = q.value
+        dist.barrier(group=group)
+        return True
+
+    def mc(self, region: str, byte_offset: int = 0) -> int:
+        """Multicast address of ``region``: a ``multimem.st`` there lands in EVERY rank's window, a ``multimem.ld_reduce``
+        sums over the ranks.  0 when the windows are not multicast-bound."""
+        return 0 if not self.mc_ptr else self.mc_ptr + self.regions[region].offset + byte_offset
 
     # -- addressing ------------------------------------------------------------------------------------------------
     def ptr(self, region: str, rank: Optional[int] = None, byte_offset: int = 0) -> int:
@@ -182,6 +291,9 @@ class SymmetricWindow:
 
     def close(self) -> None:
         L = _lib.lib()
+        if self.backing == "vmm":  # mappings are released with the process (windows live as long as the job)
+            self.local_ptr = 0
+            return
         for r, p in enumerate(self.peer_ptrs):
             if r != self.rank and p:
                 L.dtb_ipc_close_handle(ctypes.c_void_p(p))
