@@ -149,21 +149,27 @@ def run_ours(args) -> dict:
     assert device.type == "cuda", "bench.py needs a GPU"
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     B, T, K, W = args.batch_size, args.seq_len, args.steps, args.warmup
-    # seed=0: the same theta_base on every rank; dropout_seed=rank: independent dropout masks per miner
-    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0, dropout_seed=rank,
-                      fp8_forward=args.fp8_forward, dropout=args.dropout)
-    V = trainer.cfg.vocab_size
+    from distributedtraining_b200.models.transformer import build_manifest, get_config
+    man = build_manifest(get_config(args.model))
+    buffers = None
     if args.impl == "nccl":
-        ex = CollectiveExchange(trainer.man, delta_dtype=args.delta_dtype) if world > 1 else None
+        ex = CollectiveExchange(man, delta_dtype=args.delta_dtype) if world > 1 else None
         plane = "nccl all_gather / all_reduce + torch" if world > 1 else "local torch"
     elif args.impl == "nvls" and world > 1:
         from distributedtraining_b200.parallel.exchange import NvlsExchange
-        ex = NvlsExchange(trainer.man)  # uniform mixer: in-switch reduction + multicast of the new base
+        ex = NvlsExchange(man)  # uniform mixer: in-switch reduction + multicast of the new base
         plane = "NVLS (multimem.ld_reduce + multimem.st), uniform mixer"
         args.meta_steps = 0
     else:
-        ex = PeerExchange(trainer.man, delta_dtype=args.delta_dtype)
-        plane = "peer windows (sharded fused gather-avg kernels + pull all-gather, no NCCL)"
+        # the windows come first: the trainer's theta_base and bf16 compute copy LIVE in them, so that the peers' averaging
+        # kernels can land the new base there directly (multimem.st through the NVSwitch when the windows are multicast-bound)
+        ex = PeerExchange(man, delta_dtype=args.delta_dtype)
+        buffers = ex.trainer_buffers()
+        plane = f"peer windows ({ex.win.backing}, multicast={'yes' if ex.win.mc_ptr else 'no'}): sharded fused averaging kernels, no NCCL"
+    # seed=0: the same theta_base on every rank; dropout_seed=rank: independent dropout masks per miner
+    trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0, dropout_seed=rank,
+                      fp8_forward=args.fp8_forward, dropout=args.dropout, buffers=buffers)
+    V = trainer.cfg.vocab_size
     dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
     host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
     # validation set of the averager: ``val_texts`` sequences @ ``val_seq`` in batches of ``val_batch`` (the last one smaller),
@@ -224,7 +230,7 @@ def run_ours(args) -> dict:
         "detail": {"local_steps": args.local_steps, "meta_steps_in_timed_rounds": coord.meta_steps, "delta_dtype": args.delta_dtype,
                    "exchange": plane, "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward),
                    "dropout": trainer.cfg.dropout, "padding_mask": "attention_mask -> kv_len in the attention kernels",
-                   "cuda_graph": bool(trainer.use_graph),
+                   "cuda_graph": bool(trainer.use_graph), "base_broadcast": getattr(coord, "last_round_mode", None),
                    "meta": coord.meta.describe() if coord.meta is not None else None},
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},

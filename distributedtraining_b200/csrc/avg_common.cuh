@@ -61,4 +61,11 @@ DTB_DEVICE void load_delta8_plain(const void* dptr, const float* sptr, size_t e,
   }
 }
 
+// NVLS: one store replicated by the NVSwitch into every rank's window (multicast address), one load returning the sum.
+DTB_DEVICE void multimem_st_v4(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 }  // namespace dtb

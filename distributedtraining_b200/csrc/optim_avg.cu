@@ -40,7 +40,8 @@ template <int DELTA_MODE>  // 0: none, 1: fp32 delta, 2: bf16 delta
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, bf16* __restrict__ p16,
                                                     const float* __restrict__ grad, float* __restrict__ m,
                                                     float* __restrict__ v, const float* __restrict__ hyper,
-                                                    const float* __restrict__ base, void* __restrict__ delta, size_t n4) {
+                                                    const float* __restrict__ base, void* __restrict__ delta, size_t n4,
+                                                    const float* __restrict__ fresh_src) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
   const float step_size = lr * sqrtf(hyper[7]) / hyper[6];
   const float decay = 1.f - lr * wd;
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, 
       mm = reinterpret_cast<float4*>(m)[i];
       vv = reinterpret_cast<float4*>(v)[i];
     }
-    float4 p = reinterpret_cast<float4*>(master)[i];
+    // first step after a base pull: theta IS theta_base -- read it from there, so the round never has to write the master arena
+    float4 p = (fresh && fresh_src) ? reinterpret_cast<const float4*>(fresh_src)[i] : reinterpret_cast<float4*>(master)[i];
     float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* pp = &p.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -191,6 +193,8 @@ struct AvgParams {
   int ld_mode;                         // peer-load flavour, see ld_peer_v4
   uint32_t wait_value;
   const int* active;                   // optional [N] device mask (round_prepare_kernel): inactive miners are neither read nor weighted
+  float* out_mc_f32;                   // optional MULTICAST destinations: one multimem.st lands the result in every rank's
+  bf16* out_mc_bf16;                   //   window (the averaged-base broadcast rides on the averaging kernel, no second pass)
 };
 
 // Peer-load flavour (set once per process through DTB200_PEER_LD = sys | nc | weak; default sys):
@@ -325,6 +329,11 @@ __global__ void __launch_bounds__(256) gather_avg_kernel(const __grid_constant__
         }
         if (p.out_bf16[o]) *reinterpret_cast<uint4*>(p.out_bf16[o] + e) = ob;
       }
+      if (p.out_mc_f32) {
+        multimem_st_v4(p.out_mc_f32 + e, *reinterpret_cast<const uint4*>(&o0));
+        multimem_st_v4(p.out_mc_f32 + e + 4, *reinterpret_cast<const uint4*>(&o1));
+      }
+      if (p.out_mc_bf16) multimem_st_v4(p.out_mc_bf16 + e, ob);
     }
   }
   if (p.nan_flags) {
@@ -492,12 +501,12 @@ extern "C" int dtb_adam_prep(int* step, float* hyper, cudaStream_t s) {
   return KCHECK();
 }
 extern "C" int dtb_adamw(float* master, void* p16, const float* grad, float* m, float* v, const float* hyper, const float* base,
-                         void* delta, int delta_mode, size_t n, int num_sms, cudaStream_t s) {
+                         void* delta, int delta_mode, size_t n, int num_sms, cudaStream_t s, const float* fresh_src) {
   const size_t n4 = n / 4;
   const int grid = num_sms * 8;
-  if (delta_mode == 1) adamw_kernel<1><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4);
-  else if (delta_mode == 2) adamw_kernel<2><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4);
-  else adamw_kernel<0><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, nullptr, nullptr, n4);
+  if (delta_mode == 1) adamw_kernel<1><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4, fresh_src);
+  else if (delta_mode == 2) adamw_kernel<2><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, base, delta, n4, fresh_src);
+  else adamw_kernel<0><<<grid, 256, 0, s>>>(master, (bf16*)p16, grad, m, v, hyper, nullptr, nullptr, n4, fresh_src);
   return KCHECK();
 }
 extern "C" int dtb_delta_emit(const float* master, const float* base, void* out, float* scales, size_t n, int mode, int num_sms,
@@ -520,10 +529,12 @@ extern "C" int dtb_gather_avg(const void** deltas, const float** dscales, const 
                               const float* base, const float* w, const int64_t* chunk_start, const int32_t* chunk_len,
                               const int32_t* chunk_tid, int chunk_begin, int chunk_end, float** outs_f32, void** outs_bf16,
                               int n_out, int* nan_flags, int* error_flag, int N, int P, int mode, int grid, cudaStream_t s,
-                              const int32_t* chunk_ids, int unit_base, const int* active) {
+                              const int32_t* chunk_ids, int unit_base, const int* active, float* out_mc_f32, void* out_mc_bf16) {
   if (N > kMaxMiners || n_out > kMaxOut) return 3;
   AvgParams p{};
   p.active = active;
+  p.out_mc_f32 = out_mc_f32;
+  p.out_mc_bf16 = (bf16*)out_mc_bf16;
   for (int i = 0; i < N; ++i) {
     p.delta[i] = deltas[i];
     p.dscale[i] = dscales ? dscales[i] : nullptr;

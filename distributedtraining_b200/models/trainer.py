@@ -22,7 +22,8 @@ class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
                  lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
-                 dropout: Optional[float] = None, meta_dropout: bool = False, dropout_seed: Optional[int] = None):
+                 dropout: Optional[float] = None, meta_dropout: bool = False, dropout_seed: Optional[int] = None,
+                 buffers: Optional[Dict[str, torch.Tensor]] = None):
         if isinstance(model, str) and os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):
             # an HF checkpoint directory, as the reference's ``AutoModelForCausalLM.from_pretrained(model_name)`` + [PAD]
             # resize (hivetrain/training_manager.py:39-46)
@@ -41,12 +42,21 @@ class Trainer:
             _, _, a = new_model(self.cfg, seed=seed)
             init_flat = a.flat
         self.master = init_flat.to(**f32).clone()
-        self.base = self.master.clone()  # theta_base: the last pulled averaged model
+        # ``buffers``: externally owned arenas to live in -- PeerExchange.trainer_buffers() hands out the ``base`` (fp32) and
+        # ``p16`` (bf16) regions of this rank's symmetric window, so that the averaging kernels of the peers can land the new
+        # base / theta_bar DIRECTLY in the trainer's arenas (multimem.st through the NVSwitch), with no copy pass afterwards
+        buffers = buffers or {}
+        if "base" in buffers:
+            self.base = buffers["base"][:n]
+            self.base.copy_(self.master)
+        else:
+            self.base = self.master.clone()  # theta_base: the last pulled averaged model
+        self.master_stale = False  # True between a pushed base and the first optimizer step (theta == theta_base, master unwritten)
         self.grad = torch.zeros(n, **f32)
         self.m = torch.zeros(n, **f32)
         self.v = torch.zeros(n, **f32)
         if self.is_cuda:
-            self.p16 = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            self.p16 = buffers["p16"][:n] if "p16" in buffers else torch.empty(n, dtype=torch.bfloat16, device=self.device)
             ops.cast_copy(self.master, self.p16)
         else:
             self.p16 = self.master  # CPU: compute directly on the fp32 master
@@ -70,7 +80,7 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------------------
     def _step_body(self) -> torch.Tensor:
         loss = self.engine.forward_backward()
-        ops.adamw_step(self.master, self.p16 if self.is_cuda else None, self.grad, self.m, self.v, self.opt)
+        ops.adamw_step(self.master, self.p16 if self.is_cuda else None, self.grad, self.m, self.v, self.opt, fresh_src=self.base)
         self.engine.roll_fp8_scales()
         return loss
 
@@ -108,7 +118,15 @@ class Trainer:
             self.opt.host_step += 1
             loss = self.engine.loss
         self.steps_done += 1
+        self.master_stale = False
         return loss
+
+    def sync_master(self) -> None:
+        """After a pushed base (``master_stale``) theta lives in ``base`` only until the first optimizer step: materialise
+        it for anyone who reads ``master`` in between (checkpoints, hashes, eval)."""
+        if self.master_stale:
+            self.master.copy_(self.base)
+            self.master_stale = False
 
     def loss_and_grad(self, input_ids, labels: Optional[torch.Tensor] = None, zero_grad: bool = True) -> torch.Tensor:
         """Forward + backward at the CURRENT master/p16 without an optimizer step: grads land in ``self.grad``.
@@ -138,6 +156,7 @@ class Trainer:
     def emit_delta(self, out: torch.Tensor, scales: Optional[torch.Tensor] = None, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
         """delta = theta - theta_base into ``out`` (usually this rank's symmetric window); ``bad`` (int32[1]) is raised when
         the delta holds a NaN/Inf."""
+        self.sync_master()
         return ops.delta_emit(self.master, self.base, out, scales, bad)
 
     def load_base(self, new_base: torch.Tensor, lr: Optional[float] = None, reset_optimizer: bool = True) -> None:
@@ -165,6 +184,7 @@ class Trainer:
 
     def hf_state_dict(self, which: str = "master") -> Dict[str, torch.Tensor]:
         """HF / reference-format state dict of ``master`` or ``base`` (loads into ``GPT2LMHeadModel`` as is)."""
+        self.sync_master()
         return to_hf_state_dict(self.cfg, getattr(self, which).detach().float().cpu())
 
     def flat_from(self, blob) -> torch.Tensor:
@@ -172,6 +192,7 @@ class Trainer:
         return pack_any(self.man, blob, self.cfg)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
+        self.sync_master()
         return {"master": self.master, "base": self.base, "m": self.m, "v": self.v, "step": self.opt.step,
                 "hyper": self.opt.hyper}
 

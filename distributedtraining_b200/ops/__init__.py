@@ -342,8 +342,10 @@ class AdamState:
         self.host_step = 0
 
 
-def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None):
-    """One fused AdamW step over the whole arena; optionally also emits ``delta = master_new - base`` (fp32 or bf16)."""
+def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None, fresh_src=None):
+    """One fused AdamW step over the whole arena; optionally also emits ``delta = master_new - base`` (fp32 or bf16).
+    ``fresh_src``: on the FIRST step after an optimizer (re-)creation the parameters are read from there instead of from
+    ``master`` (theta == theta_base right after a pull: the round then never writes the master arena)."""
     state.host_step += 1
     if not use_kernels(master):
         h = state.host
@@ -351,6 +353,8 @@ def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None)
         if state.host_step == 1:  # first step after (re-)creation: moments are zero by definition (lazy optimizer reset)
             m.zero_()
             v.zero_()
+            if fresh_src is not None and fresh_src.data_ptr() != master.data_ptr():
+                master.copy_(fresh_src)
         ref.adamw_step(master, p16, grad, m, v, lr=h["lr"], beta1=h["beta1"], beta2=h["beta2"], eps=h["eps"],
                        weight_decay=h["weight_decay"], step=state.host_step, grad_scale=h["grad_scale"])
         if delta is not None:
@@ -361,7 +365,7 @@ def adamw_step(master, p16, grad, m, v, state: AdamState, base=None, delta=None)
     mode = 0 if delta is None else (1 if delta.dtype == torch.float32 else 2)
     _c(L.dtb_adamw(_lib.ptr(master), _lib.ptr(p16), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), _lib.ptr(state.hyper),
                    _lib.ptr(base), _lib.ptr(delta), mode, ctypes.c_size_t(master.numel()), _lib.num_sms(),
-                   _lib.stream_ptr()), "adamw")
+                   _lib.stream_ptr(), _lib.ptr(fresh_src)), "adamw")
     _tick(2)
     return master
 
@@ -442,12 +446,14 @@ def _dp(t) -> int:
 
 def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales=None, nan_flags=None, wait_flags=None,
                  wait_value=0, error_flag=None, chunk_range=None, mode=None, grid=None, chunk_ids=None, unit_base=False,
-                 active=None):
+                 active=None, mc_f32: int = 0, mc_bf16: int = 0):
     """Fused kernel (a): ``theta_new = s_j*base + sum_i w[i,j]*delta_i`` written to every destination in ``outs_*``.
 
     ``deltas`` / ``outs_*`` entries are tensors or raw (peer-mapped) device addresses.  ``chunk_range`` restricts the
     launch to a shard of the manifest's chunk table (reduce-scatter form).  ``active`` (int32 [N], device): miners whose
-    entry is 0 are neither read nor weighted (NaN / missing deltas, see :func:`round_prepare`).  See csrc/optim_avg.cu.
+    entry is 0 are neither read nor weighted (NaN / missing deltas, see :func:`round_prepare`).  ``mc_f32`` / ``mc_bf16``:
+    MULTICAST addresses (parallel/symm.py ``SymmetricWindow.mc``): the result is additionally stored with ``multimem.st``, i.e.
+    it lands in every rank's window -- the broadcast of the new base is part of the averaging kernel.  See csrc/optim_avg.cu.
     """
     N, P = w.shape
     if not isinstance(outs_f32, (list, tuple)):
@@ -481,7 +487,7 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
                     o.copy_(tmp.to(o.dtype))
                 else:
                     o[sel] = tmp[sel].to(o.dtype)
-        return outs_f32[0]
+        return outs_f32[0] if outs_f32 else None
     cs, cl, ct = manifest.seg_table(base.device)
     c0, c1 = chunk_range if chunk_range is not None else (0, cs.numel() if chunk_ids is None else chunk_ids.numel())
     if mode is None:
@@ -495,10 +501,10 @@ def weighted_avg(base, deltas, w, manifest, outs_f32, outs_bf16=None, *, dscales
         _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None, ctypes.c_uint32(wait_value),
         _lib.ptr(base), _lib.ptr(w), _lib.ptr(cs), _lib.ptr(cl), _lib.ptr(ct), c0, c1, _ptr_array(of), _ptr_array(ob),
         n_out, _lib.ptr(nan_flags), _lib.ptr(error_flag), N, P, mode, grid or _lib.num_sms() * 8, _lib.stream_ptr(),
-        _lib.ptr(chunk_ids), int(unit_base), _lib.ptr(active))
+        _lib.ptr(chunk_ids), int(unit_base), _lib.ptr(active), ctypes.c_void_p(mc_f32), ctypes.c_void_p(mc_bf16))
     _c(rc, "gather_avg")
     _tick()
-    return outs_f32[0]
+    return outs_f32[0] if outs_f32 else None
 
 
 def _first_chunk(manifest, device) -> torch.Tensor:

@@ -293,6 +293,44 @@ class PeerExchange(Exchange):
             round = after  # a newer round landed while we copied: the buffer may be torn, take the newer one
         return None
 
+    # -- push mode: the trainer LIVES in the window and the windows are multicast-bound --------------------------------------
+    def trainer_buffers(self) -> dict:
+        """``Trainer(..., buffers=ex.trainer_buffers())``: theta_base (fp32) and the bf16 compute copy are this rank's ``base`` /
+        ``base16`` window regions, so a peer's averaging kernel can land the new base in them with one ``multimem.st``."""
+        out = {"base": self.win.local("base", torch.float32)}
+        if self.with_base16:
+            out["p16"] = self.win.local("base16", torch.bfloat16)
+        return out
+
+    def adopted(self, trainer) -> bool:
+        return bool(self.with_base16 and getattr(trainer, "is_cuda", False) and trainer.base.data_ptr() == self.win.ptr("base")
+                    and trainer.p16.data_ptr() == self.win.ptr("base16"))
+
+    def can_push(self, trainer) -> bool:
+        """The averaged-base broadcast can ride on the averaging kernel (NVLS multicast stores into every rank's arenas)."""
+        return bool(self.win.mc_ptr) and self.adopted(trainer) and os.environ.get("DTB200_NO_PUSH", "0") != "1"
+
+    def push_average(self, base: torch.Tensor, deltas, dscales, w: torch.Tensor, round: int, mode: int, active=None,
+                     wait_flags=None) -> None:
+        """Reduce-scatter + BROADCAST in one kernel: this rank's shard of ``s_j*base + sum_i w_ij delta_i`` is stored with
+        ``multimem.st`` to the multicast addresses of the ``base`` (fp32) and ``base16`` (bf16) regions, i.e. it lands in
+        every rank's theta_base and compute copy; then the base flag is published.  ``deltas``: peer window pointers (uniform
+        mixer) or the local transposed shards of the learned mixer."""
+        cs, _, _ = self.man.seg_table(base.device)
+        nchunks = cs.numel()
+        per = (nchunks + self.world - 1) // self.world
+        c0, c1 = min(nchunks, self.rank * per), min(nchunks, (self.rank + 1) * per)
+        self.nan_flags.zero_()
+        ops.weighted_avg(base, deltas, w, self.man, [], None, dscales=dscales, nan_flags=self.nan_flags, wait_flags=wait_flags,
+                         wait_value=round if wait_flags is not None else 0, error_flag=self.win.error_flag, chunk_range=(c0, c1),
+                         mode=mode, active=active, mc_f32=self.win.mc("base"), mc_bf16=self.win.mc("base16"))
+        self._base_round = round + 1
+        self.win.publish(self.F_BASE, self._base_round)
+
+    def wait_base(self) -> None:
+        """Stream-ordered wait until every shard owner has published the current base round (all shards have landed here)."""
+        self.win.wait(self.F_BASE, self._base_round)
+
     def delta_is_bad(self, src: int, round: int) -> bool:
         """Host read of the NaN verdict miner ``src`` attached to its publish of ``round``."""
         return int(self.win.flags()[self.F_BAD + src].item()) == round

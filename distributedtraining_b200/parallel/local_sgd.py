@@ -102,6 +102,10 @@ class LocalSGDCoordinator:
                     ex.win.wait(ex.F_DELTA, r, self.miners)  # every miner's delta of this round has landed
                     torch.cuda.current_stream().synchronize()  # the scorer reads the flag page on the host (once per round)
                     self.validator.validate_and_score(round=r)
+            # push mode: the trainer's arenas are multicast-bound window regions and the optimizer is re-created anyway -> the
+            # broadcast of the new base is the multimem.st of the averaging kernel; nothing is pulled, nothing is copied
+            push = self.reset_optimizer and ex.can_push(t)
+            self.last_round_mode = "push (NVLS multicast stores from the averaging kernel)" if push else "pull"
             if self.learning:
                 # learned mixer on ALL ranks: delta all-to-all by pull once, then meta_steps sharded SGD steps on w
                 with self.timer.phase("meta_prepare"):
@@ -109,18 +113,29 @@ class LocalSGDCoordinator:
                 with self.timer.phase("meta_learning"):
                     self._meta_learn()
                 with self.timer.phase("gather_avg"):
-                    per = self.meta.final_average_shard(r)
+                    if push:
+                        self.meta.final_average_push(r)
+                    else:
+                        per = self.meta.final_average_shard(r)
             else:
                 # uniform mixer: w = 1/N_active (a miner whose emit kernel flagged NaN/Inf is skipped by every rank), then
                 # reduce-scatter by pull straight from the miners' windows
                 with self.timer.phase("gather_avg"):
                     active = ex.prepare_round(r, self.miners, self.w, init_w=True)
-                    per = ex.reduce_scatter_average(t.base, self.w, r, self.miners, active=active)
-            # all-gather by pull fused with the base / optimizer reset (no pushes: P2P stores are the slow direction)
+                    if push:
+                        d, s = ex._delta_ptrs(r, self.miners)
+                        ex.push_average(t.base, d, s, self.w, r, {"fp32": 0, "bf16": 1, "fp8": 2}[ex.delta_dtype_name], active=active)
+                    else:
+                        per = ex.reduce_scatter_average(t.base, self.w, r, self.miners, active=active)
             # the Adam moments are NOT rewritten: opt.reset() puts the step counter at 0 and the first step kernel treats them as
-            # zero (the "fresh" flag) -- the optimizer re-creation of the reference without 1 GB of stores per round
+            # zero and reads theta from theta_base (the "fresh" flag) -- the optimizer re-creation of the reference without stores
             with self.timer.phase("broadcast_reset"):
-                ex.all_gather_reset(t, per, reset_moments=False)
+                if push:
+                    ex.wait_base()          # every owner's shard has landed in my theta_base / bf16 copy
+                    t.master_stale = True   # theta == theta_base until the first step writes the master arena
+                else:
+                    # all-gather by pull fused with the base / master / bf16 reset (P2P stores are the slow direction)
+                    ex.all_gather_reset(t, per, reset_moments=False)
             if self.reset_optimizer:
                 t.opt.reset()
             if self.post_pull_lr is not None:

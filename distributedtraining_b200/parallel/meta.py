@@ -85,6 +85,8 @@ class DistributedMetaLearner:
         else:
             self.g = torch.zeros(man.total, **f32)
         self.engine = TransformerEngine(trainer.cfg, man, trainer.p16, self.g, rows_static, self.Tv, seed=1234 + self.rank)
+        # push mode: the trainer's arenas are window regions bound to the NVSwitch multicast object (see PeerExchange.can_push)
+        self.push = bool(self.peer and exchange.can_push(trainer))
         self.use_graph = (self.dev.type == "cuda") if use_graph is None else (use_graph and self.dev.type == "cuda")
         self._graphs = {}
         if self.peer:
@@ -111,6 +113,7 @@ class DistributedMetaLearner:
     def describe(self) -> dict:
         return {"mode": self.mode, "val_batch": [int(self.Bv), int(self.Tv)], "val_batches": len(self.val_batches),
                 "rows_per_rank": int(self.r1 - self.r0), "backend": "peer" if self.peer else "collective",
+                "theta_bar_all_gather": "multimem.st push (NVLS)" if self.push else ("pull" if self.peer else "all_reduce"),
                 "shard_elems": int(self.e1 - self.e0)}
 
     # -- round start -----------------------------------------------------------------------------------------------------
@@ -181,16 +184,25 @@ class DistributedMetaLearner:
             ex, win = self.ex, self.ex.win
             from .symm import F_G, F_GP, F_TB
             R = self.world
-            # 1. theta_bar shard from the LOCAL delta shards: fp32 -> master (shard only), bf16 -> my window + my p16
-            outs16 = [win.ptr("base16", self.rank), t.p16] if ex.with_base16 and t.is_cuda else None
-            ops.weighted_avg(t.base, self._dT_ptrs, self.w, man, [t.master], outs16, chunk_range=(self.c0, self.c1), mode=0,
-                             active=self.active)
-            if R > 1:
+            if self.push and R > 1:
+                # 1.+2. theta_bar shard from the LOCAL delta shards: fp32 -> master (shard only, scratch), bf16 -> multimem.st into
+                # EVERY rank's compute copy (the all-gather is the store of the rebuild kernel); then wait for the other shards
+                ops.weighted_avg(t.base, self._dT_ptrs, self.w, man, [t.master], None, chunk_range=(self.c0, self.c1), mode=0,
+                                 active=self.active, mc_bf16=win.mc("base16"))
                 win.publish(F_TB, tick)
-                # 2. bf16 all-gather by pull
-                ops.shard_pull16([win.ptr("base16", r) for r in range(R)], man, self.per, self.rank, t.p16,
-                                 wait_flags=[win.flag_ptr(F_TB + r) for r in range(R)], wait_value=tick,
-                                 error_flag=win.error_flag)
+                win.wait(F_TB, tick)
+            else:
+                # 1. theta_bar shard from the LOCAL delta shards: fp32 -> master (shard only), bf16 -> my window + my p16
+                own16 = win.ptr("base16", self.rank)
+                outs16 = ([own16] if t.p16.data_ptr() == own16 else [own16, t.p16]) if ex.with_base16 and t.is_cuda else None
+                ops.weighted_avg(t.base, self._dT_ptrs, self.w, man, [t.master], outs16, chunk_range=(self.c0, self.c1), mode=0,
+                                 active=self.active)
+                if R > 1:
+                    win.publish(F_TB, tick)
+                    # 2. bf16 all-gather by pull
+                    ops.shard_pull16([win.ptr("base16", r) for r in range(R)], man, self.per, self.rank, t.p16,
+                                     wait_flags=[win.flag_ptr(F_TB + r) for r in range(R)], wait_value=tick,
+                                     error_flag=win.error_flag)
             # 3. fwd/bwd on the (local rows of the) validation batch
             self._set_batch(k)
             self._fwd_bwd()
@@ -293,6 +305,12 @@ class DistributedMetaLearner:
         ex._base_round = round + 1
         win.publish(ex.F_BASE, ex._base_round)
         return self.per
+
+    def final_average_push(self, round: int) -> None:
+        """Push mode: theta_bar(w_final) of my shard goes by ``multimem.st`` into EVERY rank's theta_base and bf16 compute copy
+        (in place on my own shard) -- the averaged-base broadcast is the store of the averaging kernel."""
+        assert self.peer and self.push
+        self.ex.push_average(self.t.base, self._dT_ptrs, None, self.w, round, 0, active=self.active)
 
     def final_average_full(self, out: torch.Tensor) -> torch.Tensor:
         """Collective plane: the complete new base on every rank."""

@@ -32,8 +32,10 @@ def main(argv=None):
     ctx = build_context("miner", argv)
     cfg = ctx.config
     B = cfg.batch_size
+    # the trainer's theta_base / bf16 copy live in the symmetric window (peers land the new base there directly)
+    buffers = ctx.exchange.trainer_buffers() if isinstance(ctx.exchange, PeerExchange) else None
     trainer = Trainer(cfg.model, device=ctx.device, batch=B, seq=cfg.seq_len, lr=cfg.lr, seed=0, dropout_seed=ctx.rank,
-                      dropout=getattr(cfg, "dropout", None))
+                      dropout=getattr(cfg, "dropout", None), buffers=buffers)
     V = trainer.cfg.vocab_size
     done = maybe_resume(cfg, trainer, ctx.rank, role="colocated")
     # ---- exchange plane: the peer windows built by the runtime, or the collective (NCCL / gloo) baseline plane ----

@@ -90,8 +90,9 @@ def main():
     w_scale = float((w_ref - 1.0 / N).abs().max())
     out["w_moved"] = w_scale
 
-    def run_mode(name, exch, mode):
-        t2 = Trainer(tr.cfg, device=dev, batch=8, seq=64, seed=0, init_flat=tr.base.clone(), use_graph=False)
+    def run_mode(name, exch, mode, push=False):
+        bufs = exch.trainer_buffers() if push else None  # push mode: theta_bar lands in the window-resident bf16 copy by multimem.st
+        t2 = Trainer(tr.cfg, device=dev, batch=8, seq=64, seed=0, init_flat=tr.base.clone(), use_graph=False, buffers=bufs)
         ml = DistributedMetaLearner(t2, exch, miners, val, meta_lr=0.01, mode=mode)
         barrier_sync(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -121,7 +122,7 @@ def main():
         lo, hi = wsum.clone(), wsum.clone()
         if world > 1:
             dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        res = {"mode": ml.mode, "rows_per_rank": ml.r1 - ml.r0, "ms_per_step": med(ts[2:]) if K > 3 else med(ts), "ms_steps": [round(x, 3) for x in ts],
+        res = {"mode": ml.mode, "theta_bar_all_gather": ml.describe()["theta_bar_all_gather"], "rows_per_rank": ml.r1 - ml.r0, "ms_per_step": med(ts[2:]) if K > 3 else med(ts), "ms_steps": [round(x, 3) for x in ts],
                "ms_round_prepare_and_transpose": t_prep, "ms_final_average": t_fin,
                "w_err_vs_one_rank": float((ml.w - w_ref).abs().max()), "base_err_vs_one_rank": err_base,
                "w_identical_across_ranks": bool(lo.item() == hi.item()), "last_loss": float(ml.loss_acc[1])}
@@ -134,6 +135,9 @@ def main():
     run_mode("peer_replicate", ex, "replicate")
     if world > 1:
         run_mode("peer_dp", ex, "dp")
+        if ex.win.mc_ptr:
+            run_mode("peer_replicate_push", ex, "replicate", push=True)
+            run_mode("peer_dp_push", ex, "dp", push=True)
         if not args.skip_collective:
             cex = CollectiveExchange(tr.man)
             run_mode("nccl_replicate", cex, "replicate")

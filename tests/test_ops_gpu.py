@@ -203,8 +203,8 @@ def test_adamw_delta_reset():
     ops.adamw_step(master, p16, grad, m, v, st)
     ref.adamw_step(rm, None, grad, rmm, rv, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, step=1)
     _close(master, rm, rtol=1e-5)
-    _close(m, rmm, rtol=1e-5)
-    _close(v, rv, rtol=1e-5)
+    _close(m, rmm, rtol=1e-4)
+    _close(v, rv, rtol=1e-4)
     for dt in (torch.float32, torch.bfloat16):
         d = torch.empty(n, device=DEV, dtype=dt)
         ops.delta_emit(master, base, d)
