@@ -198,6 +198,7 @@ def run_ours(args) -> dict:
 
     # ---- warm-up (includes graph capture and one averaging round) ----
     g = run_steps(max(W, 3), dev_data.pool, 0, force_round=True)
+    trainer.step(dev_data.pool[0])  # the first step after a round has its own graph (in-GEMM flag acquires): capture it untimed too
     barrier_sync(device)
     coord.timer.summary()  # drop the warm-up round's phase events
 
@@ -231,6 +232,8 @@ def run_ours(args) -> dict:
                    "exchange": plane, "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward),
                    "dropout": trainer.cfg.dropout, "padding_mask": "attention_mask -> kv_len in the attention kernels",
                    "cuda_graph": bool(trainer.use_graph), "base_broadcast": getattr(coord, "last_round_mode", None),
+                   "first_forward_after_round": "forward GEMMs acquire the shard owners' base flags in-kernel (no wait kernel)"
+                   if coord.fused_first_forward else "wait kernel / pull pass before the step",
                    "meta": coord.meta.describe() if coord.meta is not None else None},
         "clocks": clocks, "gpu_launches": int(launches),
         "round_phase_ms_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},

@@ -449,6 +449,11 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int n, int stride, uint
   if (threadIdx.x < n) wait_flag_ge(flags + size_t(threadIdx.x) * stride, value, error_flag);
 }
 
+// Wait until flags[0..n) >= *target (target lives in device memory: the same launch serves every round of a captured graph).
+__global__ void wait_flags_dev_kernel(const uint32_t* flags, int n, const uint32_t* target, int* error_flag) {
+  if (threadIdx.x < n) wait_flag_ge(flags + threadIdx.x, *reinterpret_cast<const volatile uint32_t*>(target), error_flag);
+}
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -578,6 +583,11 @@ extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStre
 }
 extern "C" int dtb_wait_flags(const uint32_t* flags, int n, int stride, uint32_t value, int* error_flag, cudaStream_t s) {
   wait_flags_kernel<<<1, 64, 0, s>>>(flags, n, stride, value, error_flag);
+  return KCHECK();
+}
+
+extern "C" int dtb_wait_flags_dev(const uint32_t* flags, int n, const uint32_t* target, int* error_flag, cudaStream_t s) {
+  wait_flags_dev_kernel<<<1, 64, 0, s>>>(flags, n, target, error_flag);
   return KCHECK();
 }
 

@@ -72,6 +72,13 @@ struct GemmParams {
   float alpha;
   DropArgs drop;  // EPI_BIAS_RESID / EPI_RESID: out = aux + dropout(acc [+ bias])  (GPT-2 resid_pdrop)
   float* colsum;  // optional fp32 [N]: += column sums of the bf16 output (e.g. the bias gradient that equals colsum(dY))
+  // Fused broadcast -> first forward GEMM (path (b)): the B operand (a weight matrix of the NEW averaged base) is being landed
+  // in local HBM by the shard owners' averaging kernels (multimem.st through the NVSwitch).  The kernel itself acquires the
+  // owners' base flags (slots 0..ready_hi of this rank's flag page) against the device-resident target round before any
+  // thread touches the weights -- no separate wait kernel, no host involvement; nullptr = plain GEMM.
+  const uint32_t* ready_flags;
+  const uint32_t* ready_target;
+  int ready_hi;
 };
 
 // GELU (tanh form, HF "gelu_new") with MUFU.TANH in fp32.  (A packed tanh.approx.bf16x2 variant halves the MUFU count but
@@ -164,6 +171,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       tmem_alloc(tmem_ptr_smem, kTmemCols);
       tmem_relinquish();
     }
+  }
+  if (p.ready_flags != nullptr && threadIdx.x == 64) {  // an epilogue thread: warps 0 / 1 are busy with barriers and TMEM
+    const uint32_t tgt = *reinterpret_cast<const volatile uint32_t*>(p.ready_target);
+    for (int o = 0; o <= p.ready_hi; ++o) {
+      long long spins = 0;
+      while (ld_acquire_sys(p.ready_flags + o) < tgt && ++spins < (1ll << 27)) __nanosleep(100);
+    }
+    fence_proxy_async_all();  // the weights are consumed by TMA (async proxy)
   }
   tc_fence_before();
   __syncthreads();
@@ -601,6 +616,10 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
 
 // C ABI.  A: K-major => [M, K] pitch lda; MN-major => [K, M] pitch lda.  B likewise with N.  C: [M, N] pitch ldc.
 // out_f32 => C is fp32 and the tile is reduce-ADDED into it (caller zeroes C); splits > 1 requires out_f32.
+static const uint32_t* g_ready_flags = nullptr;   // one-shot, see dtb_gemm_set_ready
+static const uint32_t* g_ready_target = nullptr;
+static int g_ready_hi = 0;
+
 static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                      int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                      float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2, void* b_persist,
@@ -665,6 +684,8 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
   p.drop.scale = 1.f / (1.f - drop_p);
   if (p.drop.thr && ((N & 1) || !(epi == EPI_BIAS_RESID || epi == EPI_RESID))) return 2003;
   p.colsum = colsum;
+  p.ready_flags = g_ready_flags; p.ready_target = g_ready_target; p.ready_hi = g_ready_hi;
+  g_ready_flags = nullptr; g_ready_target = nullptr;
   if (colsum && (out_f32 || epi == EPI_BIAS_GELU)) return 2004;
   const int tiles_mg = (p.tiles_m + CL - 1) / CL;
   int total = tiles_mg * p.tiles_n * p.splits;   // work items per cluster
@@ -677,6 +698,11 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
 }
 
 // C ABI.  bf16 operands (all majors / modes) and e4m3 operands (K-major; alpha carries the product of the tensor scales).
+// one-shot: the NEXT GEMM launch acquires these flags in-kernel (see GemmParams::ready_flags)
+extern "C" int dtb_gemm_set_ready(const void* flags, const void* target, int hi) {
+  g_ready_flags = (const uint32_t*)flags; g_ready_target = (const uint32_t*)target; g_ready_hi = hi;
+  return 0;
+}
 extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                              int b_mn, int out_f32, int epi, const void* bias, const void* aux, int ldaux, void* c2, int ldc2,
                              float alpha, int splits, int num_sms, cudaStream_t stream, const void* b2, int ldb2,

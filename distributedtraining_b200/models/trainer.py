@@ -71,6 +71,8 @@ class Trainer:
         self.meta_dropout = bool(meta_dropout)
         self.use_graph = self.is_cuda if use_graph is None else (use_graph and self.is_cuda)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}  # step graphs: plain / first-step-after-a-pushed-base (in-GEMM flag waits)
+        self.ready_capable = False
         self._eval_graph: Optional[torch.cuda.CUDAGraph] = None
         self._lg_graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
@@ -84,6 +86,12 @@ class Trainer:
         self.engine.roll_fp8_scales()
         return loss
 
+    def enable_fused_first_forward(self, flags_address: int, target: torch.Tensor, chunks_per_rank: int, world: int) -> None:
+        """Path (b): after a pushed base the FIRST step runs a variant of the step graph whose forward GEMMs acquire the shard
+        owners' base flags inside the kernel (TransformerEngine.configure_ready) -- no wait kernel between round and step."""
+        self.engine.configure_ready(flags_address, target, chunks_per_rank, world)
+        self.ready_capable = self.is_cuda and not self.engine.fp8
+
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimizer step on a [B,T] batch (host-pinned or device).  Returns the device-resident mean loss."""
         if isinstance(input_ids, dict):  # miner: labels = input_ids (PAD not masked), attention_mask -> padding-masked attention
@@ -91,6 +99,10 @@ class Trainer:
         else:
             self.engine.set_batch(input_ids, labels)
         assert self.engine.n_rows == self.batch, "training batches must fill the static batch"
+        ready = bool(self.ready_capable and self.master_stale)  # first step after a pushed base: in-GEMM flag acquires
+        if self.ready_capable:
+            self.engine._ready_on = ready
+        self._graph = self._graphs.get(ready)
         if not self.use_graph:
             c0 = ops.launch_count()
             loss = self._step_body()
@@ -109,10 +121,11 @@ class Trainer:
                 self.launches_per_step = ops.launch_count() - c0
                 self.master.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.opt.step.copy_(snap[3])
                 self.opt.host_step = snap[4]
-                ops.cast_copy(self.master, self.p16)
+                ops.cast_copy(self.base if self.master_stale else self.master, self.p16)  # (stale master: theta == theta_base)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._step_body()
+                self._graphs[ready] = self._graph
                 self.opt.host_step = snap[4]
             self._graph.replay()
             self.opt.host_step += 1

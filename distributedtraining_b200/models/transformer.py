@@ -443,6 +443,39 @@ class TransformerEngine:
         self._src = None if src_flat is None else ModelParams(self.cfg, self.man, src_flat)
         self._src_flat = src_flat
 
+    # -- fused broadcast -> first forward GEMM (path (b)) -----------------------------------------------------------------
+    _FWD_GEMMS = ("qkv_w", "o_w", "fc_w", "proj_w")
+
+    def configure_ready(self, flags_address: int, target: torch.Tensor, chunks_per_rank: int, world: int) -> None:
+        """The weights of a NEW averaged base are landed in this arena by the shard owners' averaging kernels (rank k owns the
+        chunks [k*per, (k+1)*per) of the chunk table).  In ``ready`` mode every forward GEMM acquires, inside the kernel, the
+        base flags of the owners of everything that is consumed up to the next GEMM (its own weight and bias, the following
+        norm weights, ...): the arena is laid out in program order, so the owners a GEMM has to wait for are 0..need.  The
+        tensors consumed before the first GEMM (embedding tables, first norm) are covered by one tiny wait kernel."""
+        cs, _, _ = self.man.seg_table("cpu")
+        esz = self.P_flat.element_size()
+
+        def owner_before(view) -> int:  # owner of the arena element right before ``view`` starts
+            e = (view.data_ptr() - self.P_flat.data_ptr()) // esz - 1
+            if e < 0:
+                return 0
+            c = int(torch.searchsorted(cs, torch.tensor([e], dtype=cs.dtype), right=True)) - 1
+            return min(c // chunks_per_rank, world - 1)
+        order = [(l, n) for l in range(self.cfg.n_layer) for n in self._FWD_GEMMS]
+        views = [getattr(self.P.layers[l], n) for l, n in order]
+        need = {}
+        for i, key in enumerate(order):
+            need[key] = owner_before(views[i + 1]) if i + 1 < len(order) else world - 1
+        self._ready_need = need
+        self._ready_pre = owner_before(views[0])
+        self._ready_args = (flags_address, target)
+        self._ready_on = False
+
+    def _ready_for(self, l, name):
+        if not getattr(self, "_ready_on", False) or l is None:
+            return None
+        return (self._ready_args[0], self._ready_args[1], self._ready_need[(l, name)])
+
     def small_chunk_ids(self) -> torch.Tensor:
         """Chunk-table indices of the non-matrix tensors (norm weights, biases, positional table)."""
         if getattr(self, "_small_ids", None) is None:
@@ -457,7 +490,7 @@ class TransformerEngine:
         """Forward GEMM ``out = epi(a @ W^T)``: bf16 tcgen05 path, or e4m3 operands when ``fp8_forward`` is on."""
         if not self.fp8 or self._delta is not None or self._src is not None:
             g = self._w(l, name)
-            return ops.gemm(a, g.pop("b"), out, **g, **kw)
+            return ops.gemm(a, g.pop("b"), out, **g, ready=self._ready_for(l, name), **kw)
         L = self.cfg.n_layer
         slot = 8 * l + 2 * self._FP8_SLOTS[name] if l is not None else 8 * L
         sa, sw = self._sc[slot], self._sc[slot + 1]
@@ -495,6 +528,8 @@ class TransformerEngine:
         self._dropping = bool(train and self.drop_p > 0.0)
         if self._dropping:
             self.rng.advance()  # fresh masks every training forward; backward regenerates them from the same counter
+        if getattr(self, "_ready_on", False):  # embedding tables + first norm: owners 0.._ready_pre must have landed
+            ops.wait_flags_dev(self._ready_args[0], self._ready_pre + 1, self._ready_args[1])
         # the position table belongs to the small set (already base+delta in the arena): only the token rows are added here
         ops.embed_fwd(self.ids, P.wte, P.wpe, self.xs[0], *((delta.wte, None) if delta is not None else ()),
                       drop=self._drop("embd"))

@@ -73,7 +73,7 @@ def _row_major(t: torch.Tensor, what: str) -> int:
 # GEMM
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, out2=None, alpha=1.0, accumulate=False,
-         splits=0, b2=None, b_persist=None, drop=None, colsum_out=None):
+         splits=0, b2=None, b_persist=None, drop=None, colsum_out=None, ready=None):
     """out[M,N] = epi(alpha * A @ B^T) -- see :func:`reference.gemm` for the operand conventions.
 
     CUDA: persistent tcgen05/TMEM/TMA kernel (csrc/sm100_gemm.cu).  fp32 ``out`` is always reduce-ADDED by TMA
@@ -86,6 +86,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
     ``drop`` (``Drop``, residual epilogues only): ``out = aux + dropout(alpha A B^T + bias)``, mask generated in the epilogue.
     ``colsum_out`` (fp32 [N], bf16 outputs): += column sums of ``out`` from the epilogue's staged tiles (a bias gradient that
     equals colsum of this GEMM's output, without a second pass over it).
+    ``ready`` = (flags_address, target_tensor, hi): fused broadcast -> GEMM -- the kernel acquires flag slots 0..hi of this
+    rank's base-flag block against the device-resident target round before touching ``b`` (the weights of a NEW averaged base
+    that the shard owners' averaging kernels are landing in local HBM by multimem.st).
     """
     if not use_kernels(out):
         ref.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, bias=bias, aux=aux, out2=out2, alpha=alpha,
@@ -113,6 +116,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epi="none", bias=None, aux=None, 
         splits = 1
     ldaux = _row_major(aux, "aux") if aux is not None else 0
     ldc2 = _row_major(out2, "out2") if out2 is not None else 0
+    if ready is not None:
+        _lib.lib().dtb_gemm_set_ready(ctypes.c_void_p(ready[0]), _lib.ptr(ready[1]), int(ready[2]))
     rc = _lib.lib().dtb_gemm_bf16(
         _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), int(out_f32), EPI[epi],
         _lib.ptr(bias), _lib.ptr(aux), ldaux, _lib.ptr(out2), ldc2, ctypes.c_float(alpha), splits, _lib.num_sms(),
@@ -602,6 +607,13 @@ def w_update(slots, w, lr: float, *, wait_flags=None, wait_value=0, loss_acc=Non
                                _ptr_array([_dp(f) for f in wait_flags]) if wait_flags is not None else None,
                                ctypes.c_uint32(wait_value), len(slots), _lib.ptr(w), ctypes.c_float(lr), N, P, _lib.ptr(loss_acc),
                                _lib.ptr(error_flag), _lib.stream_ptr()), "w_update")
+    _tick()
+
+
+def wait_flags_dev(flags_address: int, n: int, target: torch.Tensor, error_flag=None) -> None:
+    """Stream-ordered device-side wait until flag slots 0..n-1 reach the round stored in ``target`` (device uint32/int32[1])."""
+    _c(_lib.lib().dtb_wait_flags_dev(ctypes.c_void_p(flags_address), n, _lib.ptr(target), _lib.ptr(error_flag), _lib.stream_ptr()),
+       "wait_flags_dev")
     _tick()
 
 

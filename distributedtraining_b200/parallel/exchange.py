@@ -221,6 +221,7 @@ class PeerExchange(Exchange):
         self.win = SymmetricWindow(regions, group)
         self.rank, self.world = self.win.rank, self.win.world
         self.F_DELTA, self.F_BASE, self.F_BAD = F_DELTA, F_BASE, F_BAD
+        self.base_target = torch.zeros(1, dtype=torch.int32, device=self.win.device)  # base round the next forward has to see
         self._bad = torch.zeros(1, dtype=torch.int32, device=self.win.device)      # my delta holds NaN/Inf (set by the emit kernel)
         self.active = torch.ones(max(self.world, 1), dtype=torch.int32, device=self.win.device)  # per-miner mask of the round
         self.n_active = torch.zeros(1, dtype=torch.int32, device=self.win.device)
@@ -326,6 +327,7 @@ class PeerExchange(Exchange):
                          mode=mode, active=active, mc_f32=self.win.mc("base"), mc_bf16=self.win.mc("base16"))
         self._base_round = round + 1
         self.win.publish(self.F_BASE, self._base_round)
+        self.base_target.fill_(self._base_round)  # device-resident target of the in-kernel flag acquires (first forward GEMMs)
 
     def wait_base(self) -> None:
         """Stream-ordered wait until every shard owner has published the current base round (all shards have landed here)."""

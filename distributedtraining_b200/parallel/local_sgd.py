@@ -31,7 +31,7 @@ class LocalSGDCoordinator:
                  mixer: str = "learned", meta_steps: int = 0, meta_lr: float = 0.01, val_batches: Optional[list] = None,
                  post_pull_lr: Optional[float] = 5e-5, reset_optimizer: bool = True, meta_epochs: int = 0,
                  meta_mode: str = "auto", meta_dropout: bool = False, reset_w: bool = True, meta_log=None,
-                 validator=None, validate_every: int = 0):
+                 validator=None, validate_every: int = 0, fused_first_forward: bool = True):
         self.trainer = trainer
         self.ex = exchange
         self.rank = getattr(exchange, "rank", 0)
@@ -46,6 +46,14 @@ class LocalSGDCoordinator:
         # optional co-located validator (validation_logic.CollectiveDeltaValidator): scores the round's deltas against the
         # OLD base, i.e. after the publish and before the averaging replaces theta_base
         self.validator, self.validate_every = validator, int(validate_every)
+        # path (b): after a pushed base the first forward GEMMs acquire the owners' base flags in-kernel (no wait kernel)
+        self.fused_first_forward = False
+        if fused_first_forward and isinstance(exchange, PeerExchange) and exchange.can_push(trainer) and hasattr(trainer, "engine") \
+                and exchange.world > 1:
+            nch = trainer.man.seg_table("cpu")[0].numel()
+            per = (nch + exchange.world - 1) // exchange.world
+            trainer.enable_fused_first_forward(exchange.win.flag_ptr(exchange.F_BASE), exchange.base_target, per, exchange.world)
+            self.fused_first_forward = trainer.ready_capable
         self.timer = PhaseTimer(enabled=True)  # CUDA-event phase timers (read once, at the end of a bench)
         self.round = 0
         self.round_base = 0  # rounds completed before a resume
@@ -131,7 +139,10 @@ class LocalSGDCoordinator:
             # zero and reads theta from theta_base (the "fresh" flag) -- the optimizer re-creation of the reference without stores
             with self.timer.phase("broadcast_reset"):
                 if push:
-                    ex.wait_base()          # every owner's shard has landed in my theta_base / bf16 copy
+                    if not self.fused_first_forward:
+                        ex.wait_base()      # every owner's shard has landed in my theta_base / bf16 copy
+                    # else: the first forward GEMMs of the next step acquire the owners' flags themselves (TransformerEngine.
+                    # configure_ready): the broadcast overlaps the step instead of preceding it
                     t.master_stale = True   # theta == theta_base until the first step writes the master arena
                 else:
                     # all-gather by pull fused with the base / master / bf16 reset (P2P stores are the slow direction)
@@ -175,6 +186,12 @@ class LocalSGDCoordinator:
                 new_base = self._new_base
         with self.timer.phase("broadcast_reset"):
             t.load_base(new_base, lr=self.post_pull_lr, reset_optimizer=self.reset_optimizer)
+
+    def sync_base(self) -> None:
+        """Stream-ordered wait for a pushed base to have landed completely (needed before anything but ``Trainer.step`` reads
+        the arenas right after a round in fused-first-forward mode: evaluation, checkpoints, checksums)."""
+        if isinstance(self.ex, PeerExchange) and self.ex._base_round > 0 and self.ex.world > 1:
+            self.ex.wait_base()
 
     def __call__(self, loop=None) -> None:
         self.finish_round(loop)

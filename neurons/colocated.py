@@ -77,7 +77,9 @@ def main(argv=None):
 
     def round_hook(lp):
         coord.finish_round(lp)
-        ckpt(_State(), coord.rounds_total)
+        if ckpt.every > 0 and coord.rounds_total % ckpt.every == 0:
+            coord.sync_base()  # a pushed base must have landed completely before the arenas are read for the checkpoint
+            ckpt(_State(), coord.rounds_total)
 
     max_steps = cfg.rounds * cfg.local_steps if cfg.rounds else None
     loop = DeltaLoop(ctx.device, cfg.model, train, learning_rate=cfg.lr, hf_manager=None, trainer=trainer,
@@ -90,6 +92,7 @@ def main(argv=None):
             loop.max_steps = loop.global_step + max_steps
         logger.info(f"rank {ctx.rank}: continuing after round {done}")
     loop.train(epochs=int(3e16) if max_steps is None else 1)
+    coord.sync_base()
     ckpt(_State(), coord.rounds_total, force=True)
     if isinstance(ex, PeerExchange):
         ex.win.check_errors()

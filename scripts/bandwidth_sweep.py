@@ -55,7 +55,7 @@ def main():
         base = torch.randn(n, device=dev)
         master = base + 0.01 * torch.randn(n, device=dev)
         w = torch.full((world, len(man)), 1.0 / world, device=dev)
-        ex = PeerExchange(man, delta_dtype=a.dtype, with_base16=False)
+        ex = PeerExchange(man, delta_dtype=a.dtype, with_base16=True, with_meta=False)
         tr = T(master, base)
         st = {"r": 0}
         miners = list(range(world))
@@ -85,7 +85,28 @@ def main():
             _torch_weighted_avg(base, allg, w, tid, ref)
         def nccl_allgather_only():
             dist.all_gather_into_tensor(allg.view(-1), mine)
+        # NVLS push round: reduce-scatter by pull from the miners' windows + broadcast by multimem.st FROM THE SAME KERNEL into every
+        # rank's (window-resident) fp32 base and bf16 copy, then the flag wait -- the product round when the windows are multicast-bound
+        base_win = ex.win.local("base", torch.float32)[:n]
+        base_win.copy_(base)
+        mode_id = {"fp32": 0, "bf16": 1, "fp8": 2}[a.dtype]
+        def fused_push_round():
+            st["r"] += 1
+            ex.win.publish(ex.F_DELTA, st["r"])
+            d, s = ex._delta_ptrs(st["r"], miners)
+            ex.push_average(base_win, d, s, w, st["r"], mode_id, wait_flags=[ex.win.flag_ptr(ex.F_DELTA + r) for r in miners])
+            ex.wait_base()
+        # the FAIR NCCL bar: pre-scale the local delta by its row of w, ncclAllReduce, one axpy -- 2 x (N-1)/N x bytes
+        # on the wire instead of the all_gather's (N-1) x bytes
+        scaled = torch.empty(n, dtype=torch.float32, device=dev)
+        ssum = w.sum(0)
+        def nccl_allreduce_prescaled():
+            torch.mul(mine.float() if mine.dtype != torch.float32 else mine, w[rank][tid], out=scaled)
+            dist.all_reduce(scaled)
+            torch.addcmul(scaled, base, ssum[tid], out=ref)
         base0 = base.clone()
+        t_push = timed(fused_push_round, dev) if (ex.win.mc_ptr and world > 1) else None
+        t_ar = timed(nccl_allreduce_prescaled, dev) if world > 1 else None
         t_pr = timed(fused_pull_round, dev)
         base.copy_(base0)  # the pull round adopts the new base in place; restore for the other variants
         t_sh, t_pull = timed(fused_sharded, dev), timed(fused_pull, dev)
@@ -96,6 +117,7 @@ def main():
         row = {"delta_mb_fp32": mb, "delta_bytes": bytes_delta,
                "ms_fused_pull_round_rs_plus_ag_reset": t_pr, "ms_fused_sharded_gather_avg_bcast": t_sh, "ms_fused_pull_gather_avg_rank0": t_pull,
                "ms_nccl_allgather_plus_torch_avg": t_nf, "ms_nccl_allgather_only": t_ag,
+               "ms_fused_push_round_nvls": t_push, "ms_nccl_prescale_allreduce_axpy": t_ar, "window_backing": ex.win.backing,
                "fused_sharded_ingress_gbs_per_rank": in_sharded / t_sh / 1e6 if world > 1 else None,
                "fused_pull_ingress_gbs_rank0": (world - 1) * bytes_delta / t_pull / 1e6 if world > 1 else None,
                "nccl_allgather_busbw_gbs": (world - 1) * n * mine.element_size() / t_ag / 1e6 if world > 1 else None,
@@ -107,6 +129,13 @@ def main():
         row["roofline_ms_pull_round"] = max(in_pull / (NVLINK_GBS * 1e6), 22.0 * n / (6578.7 * 1e6))
         row["fraction_of_roofline_pull_round"] = row["roofline_ms_pull_round"] / t_pr
         row["fraction_of_roofline"] = row["roofline_ms_sharded"] / t_sh
+        if t_push:
+            # push round per rank: ingress (N-1)/N delta bytes by pull + (N-1)/N x 6 B/elem landing from the switch; egress 6 B/elem x n/N
+            in_push = (world - 1) / world * (bytes_delta + n * 6)
+            row["push_round_ingress_gbs_per_rank"] = in_push / t_push / 1e6
+            row["roofline_ms_push_round"] = in_push / (NVLINK_GBS * 1e6)
+            row["fraction_of_roofline_push_round"] = row["roofline_ms_push_round"] / t_push
+            row["speedup_push_vs_fair_nccl"] = t_ar / t_push
         out["rows"].append(row)
         if rank == 0:
             print("SWEEP " + json.dumps(row), flush=True)
