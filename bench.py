@@ -222,7 +222,7 @@ def run_ours(args) -> dict:
     tokens = K * B * T * world
     desc = GPT2_SMALL_DESC if trainer.cfg.name == "gpt2" else f"{trainer.cfg.name} ({trainer.man.num_params} params, vocab {V})"
     result = {
-        "metric": "tokens/sec (GPT-2-small local-SGD training, all miners; per-miner = value / n_gpus)",
+        "metric": f"tokens/sec ({'GPT-2-small' if trainer.cfg.name == 'gpt2' else trainer.cfg.name} local-SGD training, all miners; per-miner = value / n_gpus)",
         "value": tokens / ms_total * 1e3, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic tokens (Zipf ids, right-padded), random-init weights", "impl": args.impl,

@@ -233,8 +233,35 @@ class DistributedMetaLearner:
         if self.world > 1:
             dist.all_reduce(x, group=getattr(self.ex, "group", None))
 
+    def _step_collective_cuda(self, k: int) -> None:
+        """The FAIR NCCL formulation on a GPU: the same sharded step sequence and the same local kernels (fused weighted
+        average, segmented multi-dot) -- only the communication differs: ncclAllReduce of the zero-padded bf16 theta_bar, of the
+        validation gradient (dp mode) and of the [N, P] partials, instead of peer-memory loads / multicast stores + flags."""
+        t, man = self.t, self.t.man
+        dptr = [self.dT[i].data_ptr() - 4 * self.e0 for i in range(self.N)]
+        if self.world > 1:
+            t.p16.zero_()
+        ops.weighted_avg(t.base, dptr, self.w, man, [t.master], [t.p16], chunk_range=(self.c0, self.c1), mode=0, active=self.active)
+        self._allreduce(t.p16)  # exact: every element has exactly one non-zero contributor
+        self._set_batch(k)
+        self._fwd_bwd()
+        if self.mode == "dp":
+            self._allreduce(self.g)
+        if getattr(self, "_table", None) is None:
+            self._table = torch.empty(self.N * self.P + 1, dtype=torch.float32, device=self.dev)
+            self._partial = torch.empty(max(self.c1 - self.c0, 1) * (self.N + 1), dtype=torch.float32, device=self.dev)
+        ops.seg_dot([self.g], dptr, t.base, t.master, man, [self._table], N=self.N, mode=0, chunk_range=(self.c0, self.c1),
+                    active=self.active, loss=self.engine.loss, loss_scale=1.0 if self.mode == "dp" else 1.0 / self.world,
+                    partial=self._partial)
+        self._allreduce(self._table)
+        self.w.add_(self._table[:self.N * self.P].view(self.N, self.P), alpha=-self.meta_lr)
+        self.loss_acc[0] += self._table[self.N * self.P]
+        self.loss_acc[1] = self._table[self.N * self.P]
+
     def _step_collective(self, k: int) -> None:
         t, man = self.t, self.t.man
+        if t.is_cuda and ops.have_kernels():
+            return self._step_collective_cuda(k)
         e0, e1 = self.e0, self.e1
         # 1. theta_bar shard, 2. "all-gather" = all-reduce of the zero-padded arena (exact: every element has one owner)
         keep = self.active.bool()
