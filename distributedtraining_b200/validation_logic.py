@@ -365,13 +365,16 @@ class CollectiveDeltaValidator(DeltaValidator):
         ex = self.exchange
         return int(flags[ex.F_DELTA + src]) >= round and int(flags[ex.F_BAD + src]) != round
 
-    def validate_and_score(self, round: Optional[int] = None) -> Dict[str, float]:
+    def validate_and_score(self, round: Optional[int] = None, base_changed: bool = True) -> Dict[str, float]:
+        """``base_changed=False``: theta_base is the one scored last time -- its loss is reused instead of re-evaluated (the
+        reference evaluates the base once, in the constructor, :48)."""
         import torch.distributed as dist
         ex, net = self.exchange, self.bittensor_network
         self.round = round if round is not None else self.round + 1
         r = self.round
         hot = list(net.metagraph.hotkeys)
-        jobs = list(self.miner_ranks) + [-1]            # -1 = the base model
+        reuse_base = (not base_changed) and self.base_loss == self.base_loss
+        jobs = list(self.miner_ranks) + ([] if reuse_base else [-1])   # -1 = the base model
         table = torch.zeros(len(jobs), dtype=torch.float64, device=self.evalm.device)
         flags = ex.win.flags().tolist() if hasattr(ex, "win") else None  # ONE host read of the local flag page per round
         mode = {"fp32": 0, "bf16": 1, "fp8": 2}.get(getattr(ex, "delta_dtype_name", "fp32"), 0)
@@ -390,9 +393,10 @@ class CollectiveDeltaValidator(DeltaValidator):
         if self.world > 1:
             dist.all_reduce(table, group=self.group)
         losses = table.tolist()                         # the round's single device->host read of results
-        self.base_loss = losses[-1]
-        self.base_perplexity = math.exp(min(self.base_loss, 50.0))
-        for k, src in enumerate(jobs[:-1]):
+        if not reuse_base:
+            self.base_loss = losses[-1]
+            self.base_perplexity = math.exp(min(self.base_loss, 50.0))
+        for k, src in enumerate(self.miner_ranks):
             hk = f"rank{src}" if f"rank{src}" in hot else (hot[src] if src < len(hot) else str(src))
             if valid[k]:
                 loss = losses[k]

@@ -82,7 +82,7 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            sv.validate_and_score(round=1)
+            sv.validate_and_score(round=1, base_changed=False)  # like the other single-rank modes: base loss from the constructor
             e1.record()
             torch.cuda.synchronize()
             solo = {"ms_per_miner": e0.elapsed_time(e1) / len(miners), "losses": [sv.losses[f"rank{r}"] for r in miners]}

@@ -69,3 +69,19 @@ def test_distributed_meta_learner_peer_vs_nccl_vs_sequential():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
     out = json.loads(line[-1][len("META_CHECK "):])
     assert out["all_ranks_ok"] and out["w_moved"] > 0, out
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_collective_validator_matches_serial_scoring():
+    """All ranks scoring the deltas together (large-batch, graph-captured EvalModel, verdicts from the publish flags) gives the
+    same losses as the serial apply-then-evaluate validator and as the NCCL-broadcast baseline."""
+    n = min(_ngpu(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29616", os.path.join(ROOT, "scripts", "validator_bench.py"), "--model", "gpt2-tiny",
+                        "--eval-seq", "64", "--eval-batches", "5", "--eval-rows", "20", "--miner-steps", "4"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("VALBENCH ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    out = json.loads(line[-1][len("VALBENCH "):])
+    assert out["max_loss_diff_collective_vs_applied"] < 2e-2, out
+    assert all(abs(a - b) < 2e-2 for a, b in zip(out["collective_all_ranks"]["losses"], out["nccl"]["losses"])), out
