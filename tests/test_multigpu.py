@@ -85,3 +85,15 @@ def test_collective_validator_matches_serial_scoring():
     out = json.loads(line[-1][len("VALBENCH "):])
     assert out["max_loss_diff_collective_vs_applied"] < 2e-2, out
     assert all(abs(a - b) < 2e-2 for a, b in zip(out["collective_all_ranks"]["losses"], out["nccl"]["losses"])), out
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_role_mode_peer_plane_averager_at_nonzero_rank():
+    """Miners must see (and adopt) the base published by an averager that is NOT rank 0 (advisor finding of round 1)."""
+    n = min(_ngpu(), 3)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "role_mode_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("ROLE_CHECK ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    assert json.loads(line[-1][len("ROLE_CHECK "):])["ok"]
