@@ -296,7 +296,18 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const bf16* __restrict__ 
 // with plain read-modify-writes (each lane owns fixed columns, each warp its own row -> no atomics, no register
 // accumulators), which keeps the kernel at <= 128 registers / two CTAs per SM; the first version held 72 accumulators in
 // registers (226 regs, 12 % occupancy, 41 us for 16384 x 768 -- 2.7x off the bandwidth bound, profiles/ncu_misc_v1.json).
-template <bool RMS, int VPL, bool COL>
+// PF = true (d = 768): the NEXT row of (dy, x, dresid) is brought into a per-warp staging area with cp.async while the current
+// row is processed from registers -- the kernel was latency-bound (one row per warp in flight, 19 % of the stall samples on
+// the first use of the loads, 46 % of DRAM peak: profiles/ncu_r2_norm_bwd_fast_kernel.json); the staging costs 36 KB per CTA and
+// still fits two CTAs per SM.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool RMS, int VPL, bool COL, bool PF = false>
 __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                                const bf16* __restrict__ w, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const bf16* __restrict__ dresid,
@@ -312,18 +323,43 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
   for (int i = lane; i < NACC * d; i += 32) my[i] = 0.f;
   __syncwarp();
   const uint4* wv = reinterpret_cast<const uint4*>(w);
-  for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
+  // per-warp staging of the prefetched row: [3 arrays][VPL * 32] uint4, behind the accumulators
+  uint4* stg = reinterpret_cast<uint4*>(sm + size_t(wpb) * NACC * d) + size_t(wib) * 3 * VPL * 32;
+  auto prefetch = [&](int row) {
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * d);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      cp_async16(stg + lane + 32 * j, dyr + lane + 32 * j);
+      cp_async16(stg + VPL * 32 + lane + 32 * j, xr + lane + 32 * j);
+      if (dresid) cp_async16(stg + 2 * VPL * 32 + lane + 32 * j, reinterpret_cast<const uint4*>(dresid + size_t(row) * d) + lane + 32 * j);
+    }
+  };
+  const int row0 = blockIdx.x * wpb + wib, rstep = gridDim.x * wpb;
+  if (PF && row0 < M) prefetch(row0);
+  for (int row = row0; row < M; row += rstep) {
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + size_t(row) * d);
     const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(row) * d);
     const uint4* rr = dresid ? reinterpret_cast<const uint4*>(dresid + size_t(row) * d) : nullptr;
     const float mu = RMS ? 0.f : mean[row];
     const float rs = rstd[row];
     uint4 gq[VPL], xq[VPL], rq[VPL];
+    if (PF) {
+      cp_async_commit_wait();  // this lane's chunks of the current row have landed (each lane reads back only what it copied)
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {  // every load of the row is in flight before the first use
-      gq[j] = __ldg(dyr + lane + 32 * j);
-      xq[j] = __ldg(xr + lane + 32 * j);
-      if (rr) rq[j] = __ldg(rr + lane + 32 * j);
+      for (int j = 0; j < VPL; ++j) {
+        gq[j] = stg[lane + 32 * j];
+        xq[j] = stg[VPL * 32 + lane + 32 * j];
+        if (rr) rq[j] = stg[2 * VPL * 32 + lane + 32 * j];
+      }
+      if (row + rstep < M) prefetch(row + rstep);  // overlaps the whole computation below
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {  // every load of the row is in flight before the first use
+        gq[j] = __ldg(dyr + lane + 32 * j);
+        xq[j] = __ldg(xr + lane + 32 * j);
+        if (rr) rq[j] = __ldg(rr + lane + 32 * j);
+      }
     }
     float g[VPL][8], xh[VPL][8];
     float s1 = 0.f, s2 = 0.f;
@@ -773,8 +809,9 @@ static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, 
                                   const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
                                   float* dcol, void* dxm, const DropArgs& drop) {
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
-  const size_t smem = size_t(8) * NACC * VPL * 256 * sizeof(float);
-  auto k = norm_bwd_fast_kernel<RMS, VPL, COL>;
+  constexpr bool PF = (VPL == 3);  // accumulators + staging of two CTAs fit one SM only for d = 768
+  const size_t smem = size_t(8) * NACC * VPL * 256 * sizeof(float) + (PF ? size_t(8) * 3 * VPL * 32 * 16 : 0);
+  auto k = norm_bwd_fast_kernel<RMS, VPL, COL, PF>;
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -127,8 +127,12 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
 // FP8: e4m3 operands (K-major only), kind::f8f6f4.  A TEMPLATE parameter on purpose: a runtime branch in the single-thread
 // MMA issue loop cost 20 % of the GEMM throughput (measured: 1088 -> 860 TFLOP/s on 16384x2304x768) -- the issuing thread has
 // ~128 cycles per instruction and every extra branch/select in that loop starves the tensor pipe.
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false>
+// EPIT >= 0: the epilogue mode is a compile-time constant (the hot shapes of the training step); -1: read it from the params.
+// The slab loop of the runtime version spends ~6 % of its instructions on mode branches / selects, and the fused epilogues are
+// issue-bound.
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false, int EPIT = -1>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
+  const int epi_mode = EPIT >= 0 ? EPIT : p.epi;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kNStages = CL == 2 ? kStages2 : kStages;
@@ -358,10 +362,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     const float alpha_eff = p.alpha * (p.scale_a ? (*p.scale_a) * (*p.scale_b) : 1.f);
     constexpr int kColsPerSlab = OUT_F32 ? 32 : 64;
     constexpr int kSlabs = BLOCK_N / kColsPerSlab;
-    const bool has_bias = (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID);
-    const bool has_aux = !OUT_F32 && (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID || p.epi == EPI_DGELU);
-    const bool dual = (p.epi == EPI_BIAS_GELU);
-    const uint32_t dthr = (p.epi == EPI_BIAS_RESID || p.epi == EPI_RESID) ? p.drop.thr : 0u;
+    const bool has_bias = (epi_mode == EPI_BIAS || epi_mode == EPI_BIAS_GELU || epi_mode == EPI_BIAS_RESID);
+    const bool has_aux = !OUT_F32 && (epi_mode == EPI_BIAS_RESID || epi_mode == EPI_RESID || epi_mode == EPI_DGELU);
+    const bool dual = (epi_mode == EPI_BIAS_GELU);
+    const uint32_t dthr = (epi_mode == EPI_BIAS_RESID || epi_mode == EPI_RESID) ? p.drop.thr : 0u;
     const uint32_t dkey = dthr ? drop_key(p.drop.rng, p.drop.stream) : 0u;
     auto issue_aux = [&](int w, int sl, uint32_t b) {  // issuer only: aux slab of work item (w, sl) -> staging buffer b
       const int n_t = w % p.tiles_n;
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
             if (has_aux) {
               const uint4 q = *reinterpret_cast<const uint4*>(rowp + sw);
               const float2 a[4] = {unpack_bf16x2(q.x), unpack_bf16x2(q.y), unpack_bf16x2(q.z), unpack_bf16x2(q.w)};
-              if (p.epi == EPI_DGELU) {
+              if (epi_mode == EPI_DGELU) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = __fmul2_rn(v[i], dgelu_tanh2(a[i]));
               } else {
@@ -573,9 +577,9 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inn
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false>
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false, int EPIT = -1>
 static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL, FP8>;
+  auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL, FP8, EPIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -605,6 +609,14 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
     if (!a_mn && b_mn) return launch<false, true, true, CL>(p, grid, stream);
     if (!a_mn && !b_mn) return launch<false, false, true, CL>(p, grid, stream);
     return launch<true, false, true, CL>(p, grid, stream);
+  }
+  static const bool no_spec = getenv("DTB200_GEMM_NO_EPI_SPEC") != nullptr;  // A/B switch
+  if (CL == 2 && !a_mn && !p.colsum && !p.dual_b && !p.persist_b && !no_spec) {  // the training step's hot fused-epilogue shapes
+    if (!b_mn && p.epi == EPI_BIAS) return launch<false, false, false, CL, false, EPI_BIAS>(p, grid, stream);
+    if (!b_mn && p.epi == EPI_BIAS_GELU) return launch<false, false, false, CL, false, EPI_BIAS_GELU>(p, grid, stream);
+    if (!b_mn && p.epi == EPI_BIAS_RESID) return launch<false, false, false, CL, false, EPI_BIAS_RESID>(p, grid, stream);
+    if (b_mn && p.epi == EPI_DGELU) return launch<false, true, false, CL, false, EPI_DGELU>(p, grid, stream);
+    if (b_mn && p.epi == EPI_NONE) return launch<false, true, false, CL, false, EPI_NONE>(p, grid, stream);
   }
   if (a_mn && b_mn) return launch<true, true, false, CL>(p, grid, stream);
   if (!a_mn && b_mn) return launch<false, true, false, CL>(p, grid, stream);
