@@ -57,8 +57,11 @@ class DistributedMetaLearner:
         assert self.val_batches, "the learned mixer needs validation batches"
         self.Bv = max(int(b["input_ids"].shape[0]) for b in self.val_batches)
         self.Tv = int(self.val_batches[0]["input_ids"].shape[1])
-        if mode == "auto":  # data-parallel only when every rank gets enough rows to keep its GEMMs busy
-            mode = "dp" if (self.world > 1 and self.Bv >= 4 * self.world) else "replicate"
+        if mode == "auto":
+            # data-parallel as soon as every rank gets at least one row: measured faster than replicating the batch at N = 2 and
+            # N = 8 even with ONE 512-token row per rank (5.2 vs 6.7 ms per step, profiles/meta_check_n8_gpt2_b8.json), and 6 x
+            # faster at 12 rows per rank (9.2 vs 55.9 ms, ..._b96.json); the fused reduce-scatter of g costs ~0.6 ms
+            mode = "dp" if (self.world > 1 and self.Bv >= self.world) else "replicate"
         if self.world == 1:
             mode = "replicate"
         self.mode = mode
