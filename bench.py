@@ -278,6 +278,16 @@ def run_ours(args) -> dict:
         ph = coord.timer.summary()
         coord.meta_epochs = 0
         done = coord.meta_steps_done - m0
+        # path (b): the step right after the round (its forward GEMMs acquire the owners' base flags in-kernel while the pushed
+        # shards are still landing) against an ordinary step
+        ef0, ef1, ef2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ef0.record()
+        trainer.step(dev_data.pool[0])
+        ef1.record()
+        trainer.step(dev_data.pool[1])
+        ef2.record()
+        barrier_sync(device)
+        first_ms, next_ms = max_over_ranks(ef0.elapsed_time(ef1), device), max_over_ranks(ef1.elapsed_time(ef2), device)
         result["full_round"] = {
             "measured_directly": True, "round_ms": round(ms_round, 2), "local_steps": args.local_steps,
             "mining_ms": round(ms_mine, 2), "exchange_ms": round(ms_round - ms_mine, 2), "meta_epochs": args.meta_epochs,
@@ -286,6 +296,7 @@ def run_ours(args) -> dict:
             "phase_ms_rank0": {k: round(v, 3) for k, v in ph.items()},
             "val_set": {"texts": args.val_texts, "seq": Tv, "batch": Bv, "batches": len(val)},
             "tokens_per_s_incl_averaging": round(args.local_steps * B * T * world / ms_round * 1e3, 1),
+            "first_step_after_round_ms": round(first_ms, 3), "ordinary_step_ms": round(next_ms, 3),
             "val_loss_last_step": float(coord.meta.loss_acc[1]) if coord.meta is not None else None,
             "w_mean_per_miner": [round(float(x), 5) for x in coord.w.mean(dim=1)]}
     # ---- cross-rank agreement: every rank must hold the same base after the rounds above ----

@@ -809,7 +809,10 @@ static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, 
                                   const void* dresid, void* dx, float* dw, float* db, int M, int grid, cudaStream_t s,
                                   float* dcol, void* dxm, const DropArgs& drop) {
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
-  constexpr bool PF = (VPL == 3);  // accumulators + staging of two CTAs fit one SM only for d = 768
+  // cp.async prefetch of the next row: measured SLOWER (61 vs 57.6 us for 32768 x 768, profiles/README.md) -- the staging
+  // brings the two CTAs of an SM to 225 KB of shared memory and the copy-back costs more than the latency it hides; kept as a
+  // compile-time option
+  constexpr bool PF = false;
   const size_t smem = size_t(8) * NACC * VPL * 256 * sizeof(float) + (PF ? size_t(8) * 3 * VPL * 32 * 16 : 0);
   auto k = norm_bwd_fast_kernel<RMS, VPL, COL, PF>;
   static bool cfg = false;
