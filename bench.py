@@ -272,14 +272,8 @@ def run_ours(args) -> dict:
         em.record()
         coord.finish_round()
         e1.record()
-        barrier_sync(device)
-        ms_round = max_over_ranks(e0.elapsed_time(e1), device)
-        ms_mine = max_over_ranks(e0.elapsed_time(em), device)
-        ph = coord.timer.summary()
-        coord.meta_epochs = 0
-        done = coord.meta_steps_done - m0
-        # path (b): the step right after the round (its forward GEMMs acquire the owners' base flags in-kernel while the pushed
-        # shards are still landing) against an ordinary step
+        # path (b): the step right after the round is launched WITHOUT any synchronisation in between -- its forward GEMMs acquire
+        # the owners' base flags in-kernel while the pushed shards are still landing -- and compared with the step after it
         ef0, ef1, ef2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         ef0.record()
         trainer.step(dev_data.pool[0])
@@ -288,6 +282,12 @@ def run_ours(args) -> dict:
         ef2.record()
         barrier_sync(device)
         first_ms, next_ms = max_over_ranks(ef0.elapsed_time(ef1), device), max_over_ranks(ef1.elapsed_time(ef2), device)
+        ms_round = max_over_ranks(e0.elapsed_time(e1), device)
+        ms_mine = max_over_ranks(e0.elapsed_time(em), device)
+        ph = coord.timer.summary()
+        coord.meta_epochs = 0
+        done = coord.meta_steps_done - m0
+
         result["full_round"] = {
             "measured_directly": True, "round_ms": round(ms_round, 2), "local_steps": args.local_steps,
             "mining_ms": round(ms_mine, 2), "exchange_ms": round(ms_round - ms_mine, 2), "meta_epochs": args.meta_epochs,
