@@ -437,11 +437,18 @@ struct FlagParams {
   int n;
   uint32_t value;
   const int* cond;            // optional device predicate: publish ``value`` if *cond != 0, else 0
+  uint32_t* mc_dst;           // optional MULTICAST address of the flag word: ONE release store through the NVSwitch reaches every
+                              // rank's flag page -- the same path the multimem.st DATA of the preceding kernel took, and a
+                              // release, so the flag cannot overtake the data it announces
 };
 // Publish: make all prior writes of this GPU visible system-wide, then release-store the round number to every peer.
 __global__ void publish_flag_kernel(const __grid_constant__ FlagParams p) {
   __threadfence_system();
   const uint32_t v = (p.cond == nullptr || *p.cond != 0) ? p.value : 0u;
+  if (p.mc_dst) {
+    if (threadIdx.x == 0) asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(p.mc_dst), "r"(v) : "memory");
+    return;
+  }
   if (threadIdx.x < p.n && p.dst[threadIdx.x]) st_release_sys(p.dst[threadIdx.x], v);
 }
 // Wait until all of flags[0..n) >= value (local polling).
@@ -573,11 +580,11 @@ extern "C" int dtb_set_flag_timeout_optim(double seconds) {
   const long long polls = seconds <= 0 ? (1ll << 62) : (long long)(seconds / 200e-9);
   return cudaMemcpyToSymbol(g_spin_limit, &polls, sizeof(polls)) == cudaSuccess ? 0 : 1;
 }
-extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStream_t s, const int* cond) {
+extern "C" int dtb_publish_flag(uint32_t** dsts, int n, uint32_t value, cudaStream_t s, const int* cond, void* mc_dst) {
   if (n > kMaxMiners) return 3;
   FlagParams p{};
   for (int i = 0; i < n; ++i) p.dst[i] = dsts[i];
-  p.n = n; p.value = value; p.cond = cond;
+  p.n = n; p.value = value; p.cond = cond; p.mc_dst = (uint32_t*)mc_dst;
   publish_flag_kernel<<<1, 64, 0, s>>>(p);
   return KCHECK();
 }

@@ -326,7 +326,7 @@ class PeerExchange(Exchange):
                          wait_value=round if wait_flags is not None else 0, error_flag=self.win.error_flag, chunk_range=(c0, c1),
                          mode=mode, active=active, mc_f32=self.win.mc("base"), mc_bf16=self.win.mc("base16"))
         self._base_round = round + 1
-        self.win.publish(self.F_BASE, self._base_round)
+        self.win.publish(self.F_BASE, self._base_round, multicast=True)  # same path as the multimem.st data, release-ordered
         self.base_target.fill_(self._base_round)  # device-resident target of the in-kernel flag acquires (first forward GEMMs)
 
     def wait_base(self) -> None:

@@ -192,7 +192,7 @@ class DistributedMetaLearner:
                 # EVERY rank's compute copy (the all-gather is the store of the rebuild kernel); then wait for the other shards
                 ops.weighted_avg(t.base, self._dT_ptrs, self.w, man, [t.master], None, chunk_range=(self.c0, self.c1), mode=0,
                                  active=self.active, mc_bf16=win.mc("base16"))
-                win.publish(F_TB, tick)
+                win.publish(F_TB, tick, multicast=True)  # the flag follows the multicast data through the switch (release)
                 win.wait(F_TB, tick)
             else:
                 # 1. theta_bar shard from the LOCAL delta shards: fp32 -> master (shard only), bf16 -> my window + my p16

@@ -229,14 +229,18 @@ class SymmetricWindow:
         return self.local("flags", torch.int32)
 
     # -- synchronisation -------------------------------------------------------------------------------------------
-    def publish(self, block: int, value: int, dst_ranks: Optional[List[int]] = None, cond: Optional[torch.Tensor] = None) -> None:
+    def publish(self, block: int, value: int, dst_ranks: Optional[List[int]] = None, cond: Optional[torch.Tensor] = None,
+                multicast: bool = False) -> None:
         """After all prior work on the current stream: release-store ``value`` into slot [block + my_rank] of every
         destination rank's flag page (csrc/optim_avg.cu publish_flag_kernel).  ``cond`` (device int32[1]): store ``value``
         only if it is non-zero, else 0 (a verdict computed on the device travels without a host read)."""
         dst = list(range(self.world)) if dst_ranks is None else dst_ranks
         arr = (ctypes.c_void_p * len(dst))(*[self.flag_ptr(block + self.rank, r) for r in dst])
-        _lib.check(_lib.lib().dtb_publish_flag(arr, len(dst), ctypes.c_uint32(value), _lib.stream_ptr(), _lib.ptr(cond)),
-                   "publish_flag")
+        # ``multicast``: flags that announce multimem.st DATA travel the same way -- one multimem.st.release to the multicast
+        # address of the slot (all ranks at once), ordered behind the data by the release
+        mc = self.mc("flags", 4 * (block + self.rank)) if (multicast and self.mc_ptr and dst_ranks is None) else 0
+        _lib.check(_lib.lib().dtb_publish_flag(arr, len(dst), ctypes.c_uint32(value), _lib.stream_ptr(), _lib.ptr(cond),
+                                               ctypes.c_void_p(mc)), "publish_flag")
 
     def wait(self, block: int, value: int, src_ranks: Optional[List[int]] = None) -> None:
         """Stream-ordered wait (device-side spin) until slot [block + src] >= value for every src."""
