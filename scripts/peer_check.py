@@ -69,6 +69,22 @@ def main():
         moments_cleared = bool(pt.m.abs().max().item() == 0 and pt.v.abs().max().item() == 0)
         torch.cuda.synchronize()
         ex.win.check_errors()
+        # NVLS push round on multicast-bound windows: reduce-scatter by pull + multimem.st broadcast from the same kernel
+        err_push = err_push16 = 0.0
+        if ex.win.mc_ptr and world > 1:
+            barrier_sync(dev)
+            base_win = ex.win.local("base", torch.float32)[:n]
+            base_win.copy_(base)
+            barrier_sync(dev)
+            d_, s_ = ex._delta_ptrs(r, list(range(world)))
+            ex.push_average(base_win, d_, s_, w, r, {"fp32": 0, "bf16": 1, "fp8": 2}[dt],
+                            wait_flags=[ex.win.flag_ptr(ex.F_DELTA + q) for q in range(world)])
+            ex.wait_base()
+            torch.cuda.synchronize()
+            barrier_sync(dev)
+            err_push = (base_win - ref).abs().max().item()
+            err_push16 = (ex.win.local("base16", torch.bfloat16)[:n].float() - ref).abs().max().item()
+            ex.win.check_errors()
         err_sh = (got - ref).abs().max().item()
         err_pull = (pull - ref).abs().max().item() if rank == 0 else 0.0
         b16 = ex.win.local("base16", torch.bfloat16)[:n].float()
@@ -98,11 +114,13 @@ def main():
         t_nccl = timed(nccl) if dt == "fp32" else None
         esz = {"fp32": 4, "bf16": 2, "fp8": 1}[dt]
         res = {"dtype": dt, "max_err_pull_round": err_pr, "max_err_pull_round_bf16": err_pr16, "moments_cleared": moments_cleared,
-               "max_err_sharded": err_sh, "max_err_pull": err_pull, "max_err_bf16_copy": err_b16, "ref_max": scale,
+               "max_err_sharded": err_sh, "max_err_pull": err_pull, "max_err_push_round_nvls": err_push,
+               "max_err_push_round_nvls_bf16": err_push16, "multicast": bool(ex.win.mc_ptr), "max_err_bf16_copy": err_b16, "ref_max": scale,
                "ms_fused_round": t_ours, "ms_nccl_allgather_torch_avg": t_nccl,
                "delta_bytes": n * esz, "nvlink_in_bytes_per_rank": (world - 1) * n * esz // world}
         tol = {"fp32": 1e-5, "bf16": 1e-5, "fp8": 1e-5}[dt] * max(scale, 1.0)
-        res["ok"] = bool(err_sh <= tol and err_pull <= tol and err_b16 <= 1e-2 * max(scale, 1.0) and err_pr <= tol
+        res["ok"] = bool(err_sh <= tol and err_pull <= tol and err_push <= tol and err_push16 <= 1e-2 * max(scale, 1.0)
+                         and err_b16 <= 1e-2 * max(scale, 1.0) and err_pr <= tol
                          and err_pr16 <= 1e-2 * max(scale, 1.0) and moments_cleared)
         out["results"].append(res)
         ex.win.close()
