@@ -112,6 +112,13 @@ DTB_DEVICE uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// explicit shared-memory load: through a generic pointer the bias reads compiled to LD.E.128 (generic), on which the epilogue
+// warps of the bias+GELU GEMM spent 13.5 % of their stall samples (profiles/ncu_r2_gemm_bias_gelu.json)
+DTB_DEVICE float4 lds_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
@@ -367,16 +374,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     const bool dual = (epi_mode == EPI_BIAS_GELU);
     const uint32_t dthr = (epi_mode == EPI_BIAS_RESID || epi_mode == EPI_RESID) ? p.drop.thr : 0u;
     const uint32_t dkey = dthr ? drop_key(p.drop.rng, p.drop.stream) : 0u;
-    auto issue_aux = [&](int w, int sl, uint32_t b) {  // issuer only: aux slab of work item (w, sl) -> staging buffer b
-      const int n_t = w % p.tiles_n;
-      const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
+    // work item w -> (n tile, m-tile group) WITHOUT a division per tile: the runtime divisions (I2F.RP sequences) sat at the head of
+    // every tile's epilogue (5.6 % of the stall samples); the indices advance by a fixed (quotient, remainder) step instead
+    const int step_q = num_clusters / p.tiles_n, step_n = num_clusters % p.tiles_n;
+    int cur_q = cluster_id / p.tiles_n, cur_n = cluster_id % p.tiles_n;  // q = w / tiles_n
+    auto mt_of = [&](int q) { return (OUT_F32 ? (q % tiles_mg) : q) * CL + int(cta_rank); };  // bf16 outputs: splits == 1, q < tiles_mg
+    auto issue_aux = [&](int n_t, int m_t, int sl, uint32_t b) {  // issuer only: aux slab (tile, sl) -> staging buffer b
       mbar_expect_tx(&aux_bar[b], kSlabBytes);
       tma_load_2d(b ? buf1 : buf0, &p.tmap_aux, &aux_bar[b], n_t * BLOCK_N + sl * kColsPerSlab, m_t * BLOCK_M);
     };
-    if (has_aux && issuer && cluster_id < total_work) issue_aux(cluster_id, int(grp), 0);
+    if (has_aux && issuer && cluster_id < total_work) issue_aux(cur_n, mt_of(cur_q), int(grp), 0);
     for (int w = cluster_id; w < total_work; w += num_clusters) {
-      const int n_t = w % p.tiles_n;
-      const int m_t = ((w / p.tiles_n) % tiles_mg) * CL + cta_rank;
+      const int n_t = cur_n;
+      const int m_t = mt_of(cur_q);
+      int nxt_n = cur_n + step_n, nxt_q = cur_q + step_q;  // indices of this cluster's next work item
+      if (nxt_n >= p.tiles_n) { nxt_n -= p.tiles_n; ++nxt_q; }
+      cur_n = nxt_n; cur_q = nxt_q;
       const int m0 = m_t * BLOCK_M, n0 = n_t * BLOCK_N;
       const int row = m0 + int(row_l);
       if (has_bias) {
@@ -436,11 +449,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
           }
           if (has_aux) {
             if (issuer) {  // prefetch the aux slab of the NEXT work item into the other buffer
-              int nw = w, ns = s + 2;
-              if (ns >= kSlabs) { nw = w + num_clusters; ns = int(grp); }
+              int nw = w, ns = s + 2, an = n_t, am = m_t;
+              if (ns >= kSlabs) { nw = w + num_clusters; ns = int(grp); an = nxt_n; am = mt_of(nxt_q); }
               if (nw < total_work) {
                 tma_store_wait_read<0>();  // the previous item's store (issued one TMEM read ago) has left that buffer
-                issue_aux(nw, ns, b ^ 1u);
+                issue_aux(an, am, ns, b ^ 1u);
               }
             }
             mbar_wait(&aux_bar[b], (aux_phase >> b) & 1u);
@@ -457,8 +470,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[i] = f2(__uint_as_float(r[ch * 8 + 2 * i]), __uint_as_float(r[ch * 8 + 2 * i + 1]));
             if (has_bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(smem_bias + c0 + ch * 8 + 4);
+              const float4 b0 = lds_f4(smem_bias + c0 + ch * 8);
+              const float4 b1 = lds_f4(smem_bias + c0 + ch * 8 + 4);
               v[0] = __ffma2_rn(v[0], alpha2, f2(b0.x, b0.y));
               v[1] = __ffma2_rn(v[1], alpha2, f2(b0.z, b0.w));
               v[2] = __ffma2_rn(v[2], alpha2, f2(b1.x, b1.y));
