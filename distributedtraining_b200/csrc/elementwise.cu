@@ -62,6 +62,7 @@ __global__ void rng_advance_kernel(uint32_t* rng) { rng[1] += 1u; }
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
                                  bf16* __restrict__ out, int M, int T, int d, const bf16* __restrict__ wte2,
                                  const bf16* __restrict__ wpe2, const DropArgs drop) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const int row = blockIdx.x;
   const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   const int id = ids[row];
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(256) norm_fwd_fast_kernel(const bf16* __restri
                                                             const bf16* __restrict__ b, bf16* __restrict__ out,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int M,
                                                             float eps) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   constexpr int d = VPL * 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
                                                                bf16* __restrict__ dx, float* __restrict__ dw,
                                                                float* __restrict__ db, int M, float* __restrict__ dcol,
                                                                bf16* __restrict__ dxm, const DropArgs drop) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   constexpr int d = VPL * 256;
   const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
@@ -467,6 +470,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(512, 2) ce_fwd_bwd_smem_kernel(bf16* __restrict__ logits, const int* __restrict__ targets,
                                                                float* __restrict__ losses, int V, int ldl, float grad_scale,
                                                                int write_grad) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ uint4 srow[];
   __shared__ float red[16];
   const int row = blockIdx.x;
@@ -654,6 +658,7 @@ __global__ void __launch_bounds__(512, 2) ce_fwd_bwd_kernel(bf16* __restrict__ l
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int N, int ldx,
                                                      int rows_per_block) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   __shared__ float part[8][32 * 8 + 1];
   const int cv = threadIdx.x & 31;   // column vector within the tile (8 columns each)
   const int rl = threadIdx.x >> 5;   // row lane 0..7
@@ -685,6 +690,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // SwiGLU and RoPE (Llama family)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, int M, int F) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const size_t nvec = size_t(M) * F / 8;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nvec; i += size_t(gridDim.x) * blockDim.x) {
     const size_t row = i / (F / 8), cv = i % (F / 8);
@@ -698,6 +704,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
 }
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ gu, bf16* __restrict__ dgu, int M,
                                   int F) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const size_t nvec = size_t(M) * F / 8;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nvec; i += size_t(gridDim.x) * blockDim.x) {
     const size_t row = i / (F / 8), cv = i % (F / 8);
@@ -718,6 +725,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __r
 // rotate-half RoPE applied in place to the q and k heads of packed qkv [M, (H+2Hkv)*hd]; one thread per (row, head, pair).
 __global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot, int row_stride, int hd, float log2_theta,
                             float sign) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const int half = hd / 2;
   const size_t total = size_t(M) * nheads_rot * half;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -742,6 +750,7 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot
 __global__ void __launch_bounds__(256) quant_fp8_kernel(const bf16* __restrict__ x, uint8_t* __restrict__ q,
                                                         const float* __restrict__ scale_in, float* __restrict__ amax_out,
                                                         size_t n8) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const float inv = 1.f / fmaxf(*scale_in, 1e-12f);
   float amax = 0.f;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {

@@ -99,6 +99,7 @@ DTB_DEVICE void st_swz(uint8_t* tile, int row, int ch, uint4 v) {
 constexpr int kFwdSmem = 1024 + kTile * 7 + 64;
 
 __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -388,6 +389,7 @@ DTB_DEVICE void row_stats_smem(const AttnParams& p, const uint8_t* sDO, const ui
 constexpr int kBwdKvSmem = 1024 + kTile * 10 + 128;
 
 __global__ void __launch_bounds__(128, 1) attn_bwd_kv_kernel(const __grid_constant__ AttnParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -539,6 +541,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kv_kernel(const __grid_consta
 constexpr int kBwdQSmem = 1024 + kTile * 8 + 128;
 
 __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constant__ AttnParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -676,6 +679,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
 constexpr int kFwdSmallSmem = 1024 + kTile * 3 + 64;
 
 __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_constant__ AttnParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -834,6 +838,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
 constexpr int kBwdSmallSmem = kTile * 7 + 64;
 
 __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_constant__ AttnParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;  // the dynamic window starts 1 KB-aligned (no static shared memory in this kernel)
   uint8_t* sQ = smem;

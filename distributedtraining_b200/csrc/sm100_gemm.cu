@@ -140,6 +140,7 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
 template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false, int EPIT = -1>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int epi_mode = EPIT >= 0 ? EPIT : p.epi;
+  pdl_launch_dependents();  // the NEXT kernel of the stream may begin its own prologue as soon as every CTA is past this point
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kNStages = CL == 2 ? kStages2 : kStages;
@@ -183,6 +184,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
       tmem_relinquish();
     }
   }
+  // everything above touched only shared memory, TMEM and kernel parameters; from here on global memory written by earlier
+  // kernels is read (flags, bias, operands) or overwritten (outputs): wait for the predecessor grid to complete and flush
+  pdl_wait();
   if (p.ready_flags != nullptr && threadIdx.x == 64) {  // an epilogue thread: warps 0 / 1 are busy with barriers and TMEM
     const uint32_t tgt = *reinterpret_cast<const volatile uint32_t*>(p.ready_target);
     for (int o = 0; o <= p.ready_hi; ++o) {
@@ -604,13 +608,16 @@ static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  static const bool pdl = getenv("DTB200_NO_PDL") == nullptr;  // A/B switch
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 

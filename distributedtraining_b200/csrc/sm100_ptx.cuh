@@ -16,6 +16,14 @@ namespace dtb {
 // ----------------------------------------------------------------------------------------------
 // generic helpers
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may START while
+// its predecessor in the stream is still running, once every CTA of the predecessor has executed launch_dependents (or exited);
+// it must execute griddepcontrol.wait before touching memory the predecessor reads or writes (blocks until the predecessor has
+// completed and flushed).  Used by the GEMM: its prologue (mbarrier init, TMEM allocation, descriptor prefetch, cluster sync:
+// ~3 us) overlaps the tail of the previous kernel.
+DTB_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DTB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 DTB_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 DTB_DEVICE uint32_t lane_id() { return threadIdx.x & 31u; }
 
