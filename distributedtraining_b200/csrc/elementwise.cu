@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include "dropout.cuh"
+#include "launch_pdl.cuh"
 
 namespace dtb {
 
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256) norm_fwd_fast_kernel(const bf16* __restri
                                                             float* __restrict__ mean, float* __restrict__ rstd, int M,
                                                             float eps) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: launched early (launch_pdl.cuh) -- the predecessor has completed from here on
   constexpr int d = VPL * 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fast_kernel(const bf16* __res
                                                                float* __restrict__ db, int M, float* __restrict__ dcol,
                                                                bf16* __restrict__ dxm, const DropArgs drop) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: launched early (launch_pdl.cuh) -- the predecessor has completed from here on
   constexpr int d = VPL * 256;
   const uint32_t dkey = drop.thr ? drop_key(drop.rng, drop.stream) : 0u;
   constexpr int NACC = 1 + (RMS ? 0 : 1) + (COL ? 1 : 0);
@@ -471,6 +474,7 @@ __global__ void __launch_bounds__(512, 2) ce_fwd_bwd_smem_kernel(bf16* __restric
                                                                float* __restrict__ losses, int V, int ldl, float grad_scale,
                                                                int write_grad) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: launched early (launch_pdl.cuh) -- the predecessor has completed from here on
   extern __shared__ uint4 srow[];
   __shared__ float red[16];
   const int row = blockIdx.x;
@@ -659,6 +663,7 @@ __global__ void __launch_bounds__(512, 2) ce_fwd_bwd_kernel(bf16* __restrict__ l
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int N, int ldx,
                                                      int rows_per_block) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: launched early (launch_pdl.cuh) -- the predecessor has completed from here on
   __shared__ float part[8][32 * 8 + 1];
   const int cv = threadIdx.x & 31;   // column vector within the tile (8 columns each)
   const int rl = threadIdx.x >> 5;   // row lane 0..7
@@ -803,8 +808,8 @@ extern "C" int dtb_norm_fwd(const void* x, const void* w, const void* b, void* o
   const int grid = (M + warps_per_block - 1) / warps_per_block;
 #define FASTF(V)                                                                                                            \
   if (d == V * 256) {                                                                                                       \
-    if (rms) norm_fwd_fast_kernel<true, V><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, nullptr, (bf16*)out, nullptr, rstd, M, eps); \
-    else norm_fwd_fast_kernel<false, V><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)out, mean, rstd, M, eps); \
+    if (rms) launch_pdl(norm_fwd_fast_kernel<true, V>, dim3(grid), dim3(256), 0, s, (const bf16*)x, (const bf16*)w, (const bf16*)nullptr, (bf16*)out, (float*)nullptr, rstd, M, eps); \
+    else launch_pdl(norm_fwd_fast_kernel<false, V>, dim3(grid), dim3(256), 0, s, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)out, mean, rstd, M, eps); \
     return KCHECK();                                                                                                        \
   }
   FASTF(3) FASTF(4) FASTF(8)
@@ -829,8 +834,8 @@ static void launch_norm_bwd_fast2(const void* dy, const void* x, const void* w, 
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cfg = true;
   }
-  k<<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (const bf16*)dresid, (bf16*)dx, dw, db,
-                            M, dcol, (bf16*)dxm, drop);
+  launch_pdl(k, dim3(grid), dim3(256), smem, s, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (const bf16*)dresid, (bf16*)dx,
+             dw, db, M, dcol, (bf16*)dxm, drop);
 }
 template <bool RMS, int VPL>
 static void launch_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
@@ -890,7 +895,7 @@ extern "C" int dtb_ce_fwd_bwd(void* logits, const int* targets, float* losses, i
         if (cudaFuncSetAttribute(ce_fwd_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return 2;
         configured2 = smem;
       }
-      ce_fwd_bwd_smem_kernel<<<M, 512, smem, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
+      launch_pdl(ce_fwd_bwd_smem_kernel, dim3(M), dim3(512), smem, s, (bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
     }
   } else {
     ce_fwd_bwd_kernel<false><<<M, 512, 0, s>>>((bf16*)logits, targets, losses, V, ldl, grad_scale, write_grad);
@@ -900,7 +905,7 @@ extern "C" int dtb_ce_fwd_bwd(void* logits, const int* targets, float* losses, i
 extern "C" int dtb_colsum(const void* x, float* out, int M, int N, int ldx, cudaStream_t s) {
   const int rows_per_block = 256;
   dim3 grid((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<grid, 256, 0, s>>>((const bf16*)x, out, M, N, ldx, rows_per_block);
+  launch_pdl(colsum_kernel, grid, dim3(256), 0, s, (const bf16*)x, out, M, N, ldx, rows_per_block);
   return KCHECK();
 }
 extern "C" int dtb_swiglu_fwd(const void* gu, void* out, int M, int F, int num_sms, cudaStream_t s) {

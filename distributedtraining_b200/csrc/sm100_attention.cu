@@ -22,6 +22,7 @@
 #include <math_constants.h>
 
 #include "dropout.cuh"
+#include "launch_pdl.cuh"
 #include "sm100_ptx.cuh"
 
 namespace dtb {
@@ -707,6 +708,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // PDL: launched early -- everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem = *tmem_ptr;
   const uint32_t lane_off = (uint32_t(warp) * 32u) << 16;
   constexpr uint32_t idesc_s = make_idesc(kFmtBF16, kFmtBF16, false, false, 128, 128);
@@ -869,6 +871,7 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_small_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // PDL: launched early -- everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tS = tmem, tDP = tmem + 128;
   const uint32_t tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;  // reuse S / dP after the softmax tiles are in smem
@@ -1018,7 +1021,7 @@ extern "C" int dtb_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   }
   dim3 grid((M + kBlk - 1) / kBlk, H);
   static const bool no_small = getenv("DTB200_ATTN_NO_SMALL") != nullptr;
-  if (kBlk % T == 0 && !no_small) attn_fwd_small_kernel<<<grid, 128, kFwdSmallSmem, s>>>(p);  // self-contained blocks
+  if (kBlk % T == 0 && !no_small) launch_pdl(attn_fwd_small_kernel, grid, dim3(128), kFwdSmallSmem, s, p);  // self-contained blocks
   else attn_fwd_kernel<<<grid, 128, kFwdSmem, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -1049,7 +1052,7 @@ extern "C" int dtb_attention_bwd(const void* dout, const void* qkv, const void* 
   static const bool no_small = getenv("DTB200_ATTN_NO_SMALL") != nullptr;
   if (dbias && !(kBlk % T == 0 && H == Hkv && !no_small)) return 13;  // the fold exists in the single-block kernel only
   if (kBlk % T == 0 && H == Hkv && !no_small) {
-    attn_bwd_small_kernel<<<dim3(nblk, H), 128, kBwdSmallSmem, s>>>(p);
+    launch_pdl(attn_bwd_small_kernel, dim3(nblk, H), dim3(128), kBwdSmallSmem, s, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }
   attn_bwd_kv_kernel<<<dim3(nblk, Hkv), 128, kBwdKvSmem, s>>>(p);
