@@ -59,6 +59,7 @@ def parse_args(argv=None):
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dropout", type=float, default=None, help="train-mode dropout; default = the model preset (GPT-2: 0.1, as in the reference)")
     ap.add_argument("--fp8-forward", action="store_true", help="e4m3 forward GEMMs with delayed scaling (config 4)")
+    ap.add_argument("--fp8-backward", action="store_true", help="with --fp8-forward: fp8 dgrad GEMMs (e5m2 gradients x transposed e4m3 weights)")
     return ap.parse_args(argv)
 
 
@@ -168,7 +169,7 @@ def run_ours(args) -> dict:
         plane = f"peer windows ({ex.win.backing}, multicast={'yes' if ex.win.mc_ptr else 'no'}): sharded fused averaging kernels, no NCCL"
     # seed=0: the same theta_base on every rank; dropout_seed=rank: independent dropout masks per miner
     trainer = Trainer(args.model, device=device, batch=B, seq=T, lr=args.lr, seed=0, dropout_seed=rank,
-                      fp8_forward=args.fp8_forward, dropout=args.dropout, buffers=buffers)
+                      fp8_forward=args.fp8_forward, fp8_backward=args.fp8_backward, dropout=args.dropout, buffers=buffers)
     V = trainer.cfg.vocab_size
     dev_data = SyntheticTokens(B, T, V, seed=1000 + rank, device=str(device), pool=8)
     host_data = SyntheticTokens(B, T, V, seed=2000 + rank, pool=8, pin=True)
@@ -229,7 +230,7 @@ def run_ours(args) -> dict:
         "tokens_per_s_per_miner": tokens / ms_total * 1e3 / world, "rounds_in_timed_region": rounds,
         "config": shared_config(desc, B, T, world),
         "detail": {"local_steps": args.local_steps, "meta_steps_in_timed_rounds": coord.meta_steps, "delta_dtype": args.delta_dtype,
-                   "exchange": plane, "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward),
+                   "exchange": plane, "optimizer": "fused AdamW (fp32 master, bf16 compute)", "fp8_forward": bool(args.fp8_forward), "fp8_dgrad": bool(args.fp8_backward and args.fp8_forward),
                    "dropout": trainer.cfg.dropout, "padding_mask": "attention_mask -> kv_len in the attention kernels",
                    "cuda_graph": bool(trainer.use_graph), "base_broadcast": getattr(coord, "last_round_mode", None),
                    "first_forward_after_round": "forward GEMMs acquire the shard owners' base flags in-kernel (no wait kernel)"

@@ -754,7 +754,7 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int M, int T, int nheads_rot
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) quant_fp8_kernel(const bf16* __restrict__ x, uint8_t* __restrict__ q,
                                                         const float* __restrict__ scale_in, float* __restrict__ amax_out,
-                                                        size_t n8) {
+                                                        size_t n8, int e5m2) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: a dependent GEMM may start its prologue (sm100_ptx.cuh)
   const float inv = 1.f / fmaxf(*scale_in, 1e-12f);
   float amax = 0.f;
@@ -766,12 +766,32 @@ __global__ void __launch_bounds__(256) quant_fp8_kernel(const bf16* __restrict__
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       amax = fmaxf(amax, fabsf(a[k]));
-      b[k] = __nv_cvt_float_to_fp8(a[k] * inv, __NV_SATFINITE, __NV_E4M3);
+      b[k] = e5m2 ? __nv_cvt_float_to_fp8(a[k] * inv, __NV_SATFINITE, __NV_E5M2) : __nv_cvt_float_to_fp8(a[k] * inv, __NV_SATFINITE, __NV_E4M3);
     }
     reinterpret_cast<uint2*>(q)[i] = o;
   }
   amax = warp_max(amax);
   if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(amax));  // amax >= 0
+}
+
+// Transposing quantiser: x [R, C] bf16 -> q [C, R] e4m3 with the SAME per-tensor scale as the row-major copy.  The fp8 dgrad
+// dX = dY W needs the weight as a K-major B operand with K = out features, i.e. W^T stored row-major (the fp8 GEMM takes K-major
+// operands only); 32 x 32 tiles through shared memory, coalesced on both sides.
+__global__ void __launch_bounds__(256) quant_fp8_transpose_kernel(const bf16* __restrict__ x, uint8_t* __restrict__ q,
+                                                                  const float* __restrict__ scale_in, int R, int C) {
+  __shared__ uint8_t tile[32][33];
+  const float inv = 1.f / fmaxf(*scale_in, 1e-12f);
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? __nv_cvt_float_to_fp8(__bfloat162float(x[size_t(r) * C + c]) * inv, __NV_SATFINITE, __NV_E4M3) : 0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) q[size_t(c) * R + r] = tile[tx][j];
+  }
 }
 
 }  // namespace dtb
@@ -921,7 +941,12 @@ extern "C" int dtb_rope(void* qkv, int M, int T, int nheads_rot, int row_stride,
   rope_kernel<<<num_sms * 8, 256, 0, s>>>((bf16*)qkv, M, T, nheads_rot, row_stride, hd, log2f(theta), inverse ? -1.f : 1.f);
   return KCHECK();
 }
-extern "C" int dtb_quant_fp8(const void* x, void* q, const float* scale_in, float* amax_out, size_t n, int num_sms, cudaStream_t s) {
-  quant_fp8_kernel<<<num_sms * 8, 256, 0, s>>>((const bf16*)x, (uint8_t*)q, scale_in, amax_out, n / 8);
+extern "C" int dtb_quant_fp8(const void* x, void* q, const float* scale_in, float* amax_out, size_t n, int num_sms, cudaStream_t s,
+                             int e5m2) {
+  quant_fp8_kernel<<<num_sms * 8, 256, 0, s>>>((const bf16*)x, (uint8_t*)q, scale_in, amax_out, n / 8, e5m2);
+  return KCHECK();
+}
+extern "C" int dtb_quant_fp8_t(const void* x, void* q, const float* scale_in, int R, int C, cudaStream_t s) {
+  quant_fp8_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), 256, 0, s>>>((const bf16*)x, (uint8_t*)q, scale_in, R, C);
   return KCHECK();
 }

@@ -137,7 +137,7 @@ DTB_DEVICE float2 unpack_bf16x2(uint32_t u) {
 // EPIT >= 0: the epilogue mode is a compile-time constant (the hot shapes of the training step); -1: read it from the params.
 // The slab loop of the runtime version spends ~6 % of its instructions on mode branches / selects, and the fused epilogues are
 // issue-bound.
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false, int EPIT = -1>
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, int FP8 = 0, int EPIT = -1>
 __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int epi_mode = EPIT >= 0 ? EPIT : p.epi;
   pdl_launch_dependents();  // the NEXT kernel of the stream may begin its own prologue as soon as every CTA is past this point
@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) sm100_gemm_kernel(const __grid
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = FP8 ? make_idesc(kFmtE4M3, kFmtE4M3, false, false, BLOCK_M * CL, BLOCK_N)
+    // FP8 = 1: e4m3 x e4m3 (forward);  FP8 = 2: A in e5m2 (gradients: range over precision), B in e4m3 (weights) -- dgrad
+    constexpr uint32_t idesc = FP8 ? make_idesc(FP8 == 2 ? kFmtE5M2 : kFmtE4M3, kFmtE4M3, false, false, BLOCK_M * CL, BLOCK_N)
                                    : make_idesc(kFmtBF16, kFmtBF16, A_MN, B_MN, BLOCK_M * CL, BLOCK_N);
     // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 64-element atoms along MN are
     // BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B apart (SBO).
@@ -594,7 +595,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inn
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
-template <bool A_MN, bool B_MN, bool OUT_F32, int CL, bool FP8 = false, int EPIT = -1>
+template <bool A_MN, bool B_MN, bool OUT_F32, int CL, int FP8 = 0, int EPIT = -1>
 static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = sm100_gemm_kernel<A_MN, B_MN, OUT_F32, CL, FP8, EPIT>;
   static bool configured = false;
@@ -623,7 +624,8 @@ static cudaError_t launch(const GemmParams& p, int grid, cudaStream_t stream) {
 
 template <int CL>
 static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn, bool out_f32, cudaStream_t stream) {
-  if (p.fp8) return launch<false, false, false, CL, true>(p, grid, stream);
+  if (p.fp8 == 2) return launch<false, false, false, CL, 2>(p, grid, stream);
+  if (p.fp8) return launch<false, false, false, CL, 1>(p, grid, stream);
   if (out_f32) {
     if (a_mn && b_mn) return launch<true, true, true, CL>(p, grid, stream);
     if (!a_mn && b_mn) return launch<false, true, true, CL>(p, grid, stream);
@@ -633,10 +635,10 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
   static const bool no_spec = getenv("DTB200_GEMM_NO_EPI_SPEC") != nullptr;  // A/B switch
   if (CL == 2 && !a_mn && !p.colsum && !p.dual_b && !p.persist_b && !no_spec) {  // the training step's hot fused-epilogue shapes
     if (!b_mn && p.epi == EPI_BIAS) return launch<false, false, false, CL, false, EPI_BIAS>(p, grid, stream);
-    if (!b_mn && p.epi == EPI_BIAS_GELU) return launch<false, false, false, CL, false, EPI_BIAS_GELU>(p, grid, stream);
-    if (!b_mn && p.epi == EPI_BIAS_RESID) return launch<false, false, false, CL, false, EPI_BIAS_RESID>(p, grid, stream);
-    if (b_mn && p.epi == EPI_DGELU) return launch<false, true, false, CL, false, EPI_DGELU>(p, grid, stream);
-    if (b_mn && p.epi == EPI_NONE) return launch<false, true, false, CL, false, EPI_NONE>(p, grid, stream);
+    if (!b_mn && p.epi == EPI_BIAS_GELU) return launch<false, false, false, CL, 0, EPI_BIAS_GELU>(p, grid, stream);
+    if (!b_mn && p.epi == EPI_BIAS_RESID) return launch<false, false, false, CL, 0, EPI_BIAS_RESID>(p, grid, stream);
+    if (b_mn && p.epi == EPI_DGELU) return launch<false, true, false, CL, 0, EPI_DGELU>(p, grid, stream);
+    if (b_mn && p.epi == EPI_NONE) return launch<false, true, false, CL, 0, EPI_NONE>(p, grid, stream);
   }
   if (a_mn && b_mn) return launch<true, true, false, CL>(p, grid, stream);
   if (!a_mn && b_mn) return launch<false, true, false, CL>(p, grid, stream);
@@ -648,6 +650,7 @@ static cudaError_t dispatch(const GemmParams& p, int grid, bool a_mn, bool b_mn,
 
 // C ABI.  A: K-major => [M, K] pitch lda; MN-major => [K, M] pitch lda.  B likewise with N.  C: [M, N] pitch ldc.
 // out_f32 => C is fp32 and the tile is reduce-ADDED into it (caller zeroes C); splits > 1 requires out_f32.
+static int g_fp8_a_e5m2 = 0;                       // one-shot: the next fp8 GEMM reads its A operand as e5m2 (dgrad)
 static const uint32_t* g_ready_flags = nullptr;   // one-shot, see dtb_gemm_set_ready
 static const uint32_t* g_ready_target = nullptr;
 static int g_ready_hi = 0;
@@ -695,7 +698,8 @@ static int gemm_impl(int esz, const void* a, const void* b, void* c, int M, int 
   p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   p.num_kb = (K + KBLK - 1) / KBLK;
   p.kblk = KBLK;
-  p.fp8 = esz == 1;
+  p.fp8 = esz == 1 ? (g_fp8_a_e5m2 ? 2 : 1) : 0;
+  g_fp8_a_e5m2 = 0;
   p.c2 = reinterpret_cast<__nv_bfloat16*>(c2);
   p.ldc2 = ldc2;
   p.scale_a = scale_a;
@@ -741,6 +745,10 @@ extern "C" int dtb_gemm_bf16(const void* a, const void* b, void* c, int M, int N
                              void* b_persist, int ldbp, const void* rng, int drop_stream, float drop_p, float* colsum) {
   return gemm_impl(2, a, b, c, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_f32, epi, bias, aux, ldaux, c2, ldc2, alpha, splits, num_sms,
                    stream, b2, ldb2, b_persist, ldbp, nullptr, nullptr, rng, drop_stream, drop_p, colsum);
+}
+extern "C" int dtb_gemm_fp8_a_e5m2() {  // call right before dtb_gemm_fp8: A (an activation GRADIENT) is e5m2, B (a weight) e4m3
+  g_fp8_a_e5m2 = 1;
+  return 0;
 }
 extern "C" int dtb_gemm_fp8(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, int epi,
                             const void* bias, const void* aux, int ldaux, void* c2, int ldc2, float alpha, int num_sms,

@@ -23,7 +23,7 @@ class Trainer:
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
                  lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
                  dropout: Optional[float] = None, meta_dropout: bool = False, dropout_seed: Optional[int] = None,
-                 buffers: Optional[Dict[str, torch.Tensor]] = None):
+                 buffers: Optional[Dict[str, torch.Tensor]] = None, fp8_backward: bool = False):
         if isinstance(model, str) and os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):
             # an HF checkpoint directory, as the reference's ``AutoModelForCausalLM.from_pretrained(model_name)`` + [PAD]
             # resize (hivetrain/training_manager.py:39-46)
@@ -62,7 +62,7 @@ class Trainer:
             self.p16 = self.master  # CPU: compute directly on the fp32 master
         self.opt = ops.AdamState(self.device, lr, betas[0], betas[1], eps, weight_decay)
         self.engine = TransformerEngine(self.cfg, self.man, self.p16, self.grad, batch, seq, lm_chunk=lm_chunk,
-                                        fp8_forward=fp8_forward and self.is_cuda,
+                                        fp8_forward=fp8_forward and self.is_cuda, fp8_backward=fp8_backward and self.is_cuda,
                                         seed=seed if dropout_seed is None else dropout_seed)
         # ``seed`` fixes the (shared) initial weights; ``dropout_seed`` decorrelates the dropout masks of co-located miners
         # (every rank is built with seed=0 so that all share theta_base -- their masks must still differ: pass the rank)

@@ -287,7 +287,8 @@ class TransformerEngine:
     """Static-buffer forward/backward.  ``params`` is the compute-dtype arena (bf16 on GPU), ``grads`` the fp32 arena."""
 
     def __init__(self, cfg: ModelConfig, manifest: Manifest, params: torch.Tensor, grads: Optional[torch.Tensor],
-                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False, seed: int = 0, eval_only: bool = False):
+                 batch: int, seq: int, lm_chunk: int = 8192, fp8_forward: bool = False, seed: int = 0, eval_only: bool = False,
+                 fp8_backward: bool = False):
         self.cfg, self.man = cfg, manifest
         # eval_only: forward passes only -> ONE set of per-layer activation buffers shared by all layers (the validator scores
         # 51 200 tokens per miner: per-layer buffers for GPT-2-medium would be 40 GB, shared ones 1.7 GB)
@@ -358,8 +359,11 @@ class TransformerEngine:
         # forward GEMM operands are quantised (weights once per step, activations by a one-pass quantise kernel that also
         # collects the amax for the NEXT step); backward GEMMs stay bf16.  All scales live in two device vectors.
         self.fp8 = bool(fp8_forward)
+        # fp8 DGRAD (dX = dY W): dY quantised to e5m2 (range over precision, delayed scaling), W read from a TRANSPOSED e4m3 copy
+        # (the fp8 GEMM takes K-major operands, and K = out features here); wgrad and the LM head stay bf16
+        self.fp8_bwd = bool(fp8_backward) and self.fp8 and grads is not None
         if self.fp8:
-            n_sc = 8 * L + 2
+            n_sc = 12 * L + 2 if self.fp8_bwd else 8 * L + 2
             self._scales = torch.full((n_sc,), 8.0 / 448.0, dtype=f32, device=self.dev)
             self._amaxes = torch.zeros(n_sc, dtype=f32, device=self.dev)
 
@@ -370,7 +374,17 @@ class TransformerEngine:
             self._sc = [sc(i) for i in range(n_sc)]
             self.w8 = torch.zeros(manifest.total, dtype=torch.uint8, device=self.dev)
             self.P8 = ModelParams(cfg, manifest, self.w8)
-            self.a8 = torch.empty(M * max(Fd, d, cfg.n_head * cfg.head_dim), dtype=torch.uint8, device=self.dev)
+            self.a8 = torch.empty(M * max(2 * Fd if glu else Fd, d, cfg.qkv_dim), dtype=torch.uint8, device=self.dev)
+            self._fmax = torch.full((n_sc,), 448.0, dtype=f32, device=self.dev)  # format maximum per scale slot
+            if self.fp8_bwd:
+                self._fmax[8 * L + 2:] = 57344.0  # e5m2 slots of the activation gradients
+                self._scales[8 * L + 2:] = 1e-4    # first-step guess for gradient magnitudes (replaced by the measured amax)
+                self.w8t = torch.zeros(manifest.total, dtype=torch.uint8, device=self.dev)
+
+                def tview(w):  # [in, out] view over the arena range of weight ``w`` ([out, in], contiguous rows)
+                    off = (w.data_ptr() - self.P_flat.data_ptr()) // self.P_flat.element_size()
+                    return self.w8t[off:off + w.numel()].view(w.shape[1], w.shape[0])
+                self.W8T = [{n: tview(getattr(self.P.layers[l], n)) for n in self._FP8_SLOTS} for l in range(L)]
         self.targets = torch.full((batch, seq), -1, dtype=torch.int32, device=self.dev)
         self.ids = torch.zeros((batch, seq), dtype=torch.int32, device=self.dev)
         # un-padded keys per sequence (HF attention_mask of a right-padded batch); = T when no mask is given.  Always passed
@@ -498,15 +512,32 @@ class TransformerEngine:
         w8 = getattr(self.P8.layers[l], name) if l is not None else self.P8.wte
         if self._w8_stale:
             ops.quantize_fp8(w, w8, sw)
+            if self.fp8_bwd and l is not None:
+                ops.quantize_fp8_t(w, self.W8T[l][name], sw)  # same scale, transposed layout: B operand of the dgrad
         a8 = self.a8[:a.numel()].view(a.shape)
         ops.quantize_fp8(a, a8, sa)
         return ops.gemm_fp8(a8, w8, out, sa, sw, **kw)
+
+    _DY_SLOTS = {"proj_w": 0, "fc_w": 1, "o_w": 2, "qkv_w": 3}
+
+    def _dgemm(self, l: int, name: str, dy, out, **kw):
+        """Backward data GEMM ``out = epi(dy @ W)``: bf16 (W read MN-major), or fp8 -- dy -> e5m2, W^T from the transposed e4m3
+        copy written by this step's forward."""
+        w = getattr(self.P.layers[l], name)
+        if not self.fp8_bwd:
+            return ops.gemm(dy, w, out, b_mn=True, **kw)
+        L = self.cfg.n_layer
+        sdy = self._sc[8 * L + 2 + 4 * l + self._DY_SLOTS[name]]
+        sw = self._sc[8 * l + 2 * self._FP8_SLOTS[name] + 1]
+        dy8 = self.a8[:dy.numel()].view(dy.shape)
+        ops.quantize_fp8(dy, dy8, sdy, e5m2=True)
+        return ops.gemm_fp8(dy8, self.W8T[l][name], out, sdy, sw, a_e5m2=True, **kw)
 
     def roll_fp8_scales(self) -> None:
         """Delayed scaling: scale <- amax / 448 for the next step (3 vectorised device ops for all tensors)."""
         if self.fp8:
             torch.clamp(self._amaxes, min=1e-8, out=self._scales)
-            self._scales.mul_(1.0 / 448.0)
+            self._scales.div_(self._fmax)
             self._amaxes.zero_()
 
     def _w(self, l: Optional[int], name: str) -> dict:
@@ -617,12 +648,12 @@ class TransformerEngine:
             dy = dm if dm is not None else dx
             # ---- MLP block ----
             if cfg.family == "gpt2":
-                ops.gemm(dy, Lp.proj_w, self.du, b_mn=True, epi="dgelu", aux=self.u[l])
+                self._dgemm(l, "proj_w", dy, self.du, epi="dgelu", aux=self.u[l])
             else:
-                ops.gemm(dy, Lp.proj_w, self.dact, b_mn=True)
+                self._dgemm(l, "proj_w", dy, self.dact)
                 ops.swiglu_bwd(self.dact, self.u[l], self.du)
             ops.gemm(dy, self.act[l], Lg.proj_w, a_mn=True, b_mn=True, accumulate=True)
-            ops.gemm(self.du, Lp.fc_w, self.dh, b_mn=True)
+            self._dgemm(l, "fc_w", self.du, self.dh)
             ops.gemm(self.du, self.h2[l], Lg.fc_w, a_mn=True, b_mn=True, accumulate=True)
             if Lg.fc_b is not None:
                 # (folding this column sum into the dgelu GEMM's epilogue -- ops.gemm(colsum_out=...) -- was measured slower:
@@ -634,14 +665,14 @@ class TransformerEngine:
             dm, dm2 = dm2, dm
             dy = dm if dm is not None else dx
             # ---- attention block ----
-            ops.gemm(dy, Lp.o_w, self.datt, b_mn=True)
+            self._dgemm(l, "o_w", dy, self.datt)
             ops.gemm(dy, self.att[l], Lg.o_w, a_mn=True, b_mn=True, accumulate=True)
             # d(qkv bias) = colsum(dqkv) rides on the attention backward (GPT-2 has no RoPE between the two)
             ops.attention_bwd(self.datt, self.qkv[l], self.att[l], self.lse[l], self.dqkv, B, T, H, hd, Hkv,
                               drop=self._drop("attn", l), dbias=Lg.qkv_b, kv_len=self.kvlen)
             if cfg.family == "llama":
                 ops.rope_(self.dqkv, B, T, H, Hkv, hd, cfg.rope_theta, inverse=True)
-            ops.gemm(self.dqkv, Lp.qkv_w, self.dh, b_mn=True)
+            self._dgemm(l, "qkv_w", self.dqkv, self.dh)
             ops.gemm(self.dqkv, self.h1[l], Lg.qkv_w, a_mn=True, b_mn=True, accumulate=True)
             nxt = l - 1
             self._norm_bwd(self.dh, self.xs[l], Lp.ln1_w, self.mean1[l], self.rstd1[l], dx2, Lg.ln1_w, Lg.ln1_b, dx,

@@ -144,27 +144,47 @@ class Fp8Scale:
         self.amax.zero_()
 
 
-def quantize_fp8(x, q, st: "Fp8Scale"):
-    """q (uint8 storage of e4m3) = sat(x / st.scale); st.amax = max(st.amax, max|x|).  One pass."""
+E5M2_MAX = 57344.0
+
+
+def quantize_fp8(x, q, st: "Fp8Scale", e5m2: bool = False):
+    """q (uint8 storage of e4m3, or e5m2 for gradients) = sat(x / st.scale); st.amax = max(st.amax, max|x|).  One pass."""
     if not use_kernels(x):
         st.amax.copy_(torch.maximum(st.amax, x.float().abs().max().reshape(1)))
-        q.view(torch.float8_e4m3fn).copy_((x.float() / st.scale).clamp(-448, 448).to(torch.float8_e4m3fn))
+        dt, mx = (torch.float8_e5m2, E5M2_MAX) if e5m2 else (torch.float8_e4m3fn, 448.0)
+        q.view(dt).copy_((x.float() / st.scale).clamp(-mx, mx).to(dt))
         return q
     _c(_lib.lib().dtb_quant_fp8(_lib.ptr(x), _lib.ptr(q), _lib.ptr(st.scale), _lib.ptr(st.amax), ctypes.c_size_t(x.numel()),
-                                _lib.num_sms(), _lib.stream_ptr()), "quant_fp8")
+                                _lib.num_sms(), _lib.stream_ptr(), int(e5m2)), "quant_fp8")
     _tick()
     return q
 
 
-def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=None, aux=None, out2=None, drop=None):
-    """out[M,N] (bf16) = epi(sa*sb * A8 @ B8^T) with e4m3 operands (K-major), fp32 accumulation on kind::f8f6f4 tensor cores."""
+def quantize_fp8_t(w, q_t, st: "Fp8Scale"):
+    """q_t [C, R] (e4m3) = sat(w [R, C] / st.scale)^T -- the transposed fp8 copy of a weight (K-major B operand of the fp8 dgrad)."""
+    R, C = w.shape
+    assert tuple(q_t.shape) == (C, R)
+    if not use_kernels(w):
+        q_t.view(torch.float8_e4m3fn).copy_((w.float() / st.scale).clamp(-448, 448).to(torch.float8_e4m3fn).t())
+        return q_t
+    _c(_lib.lib().dtb_quant_fp8_t(_lib.ptr(w), _lib.ptr(q_t), _lib.ptr(st.scale), R, C, _lib.stream_ptr()), "quant_fp8_t")
+    _tick()
+    return q_t
+
+
+def gemm_fp8(a8, b8, out, sa: "Fp8Scale", sb: "Fp8Scale", *, epi="none", bias=None, aux=None, out2=None, drop=None,
+             a_e5m2: bool = False):
+    """out[M,N] (bf16) = epi(sa*sb * A8 @ B8^T) with fp8 operands (K-major), fp32 accumulation on kind::f8f6f4 tensor cores.
+    A is e4m3 (forward activations) or, with ``a_e5m2``, e5m2 (activation gradients in the dgrad); B (a weight) is e4m3."""
     if not use_kernels(out):
-        A = a8.view(torch.float8_e4m3fn).float() * sa.scale
+        A = a8.view(torch.float8_e5m2 if a_e5m2 else torch.float8_e4m3fn).float() * sa.scale
         B = b8.view(torch.float8_e4m3fn).float() * sb.scale
         return ref.gemm(A, B, out, epi=epi, bias=bias, aux=aux, out2=out2, drop=drop)
     M, K = a8.shape
     N = b8.shape[0]
     assert b8.shape[1] == K and out.dtype == torch.bfloat16 and K % 16 == 0
+    if a_e5m2:
+        _lib.lib().dtb_gemm_fp8_a_e5m2()
     rc = _lib.lib().dtb_gemm_fp8(_lib.ptr(a8), _lib.ptr(b8), _lib.ptr(out), M, N, K, a8.stride(0), b8.stride(0), out.stride(0),
                                  EPI[epi], _lib.ptr(bias), _lib.ptr(aux), _row_major(aux, "aux") if aux is not None else 0,
                                  _lib.ptr(out2), _row_major(out2, "out2") if out2 is not None else 0, ctypes.c_float(1.0),

@@ -160,6 +160,33 @@ def test_fp8_forward_trains_close_to_bf16():
     assert max(abs(a - b) for a, b in zip(res[False], res[True])) < 0.15, (res[False], res[True])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gpt2-tiny", "llama-tiny"])
+def test_fp8_backward_grads_close_to_bf16(model):
+    """fp8 dgrad (dY quantised to e5m2 x the TRANSPOSED e4m3 weight copy): the gradient arena stays aligned with the bf16
+    engine's (cosine per tensor), and a short run still learns at the same pace."""
+    torch.manual_seed(0)
+    V = get_config(model).vocab_size
+    ids = [torch.randint(0, V - 1, (8, 64), dtype=torch.int32, device="cuda") for _ in range(4)]
+    tr = {k: Trainer(model, device="cuda", batch=8, seq=64, lr=1e-3, seed=1, use_graph=False, dropout=0.0, fp8_forward=k > 0, fp8_backward=k > 1)
+          for k in (0, 1, 2)}
+    for k in tr:  # two passes: the first only collects amax (delayed scaling), the second uses rolled scales
+        for _ in range(3):
+            tr[k].loss_and_grad(ids[0])
+            if k:
+                tr[k].engine.roll_fp8_scales()
+    man = tr[0].man
+    worst = 1.0
+    for i in range(len(man)):
+        a, b = man.view(tr[0].grad, i).float().flatten(), man.view(tr[2].grad, i).float().flatten()
+        if a.norm() > 0:
+            worst = min(worst, float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)))
+    assert worst > 0.97, worst
+    res = {k: [float(tr[k].step(ids[i % 4])) for i in range(12)] for k in tr}
+    assert res[2][-1] < res[2][0]
+    assert max(abs(a - b) for a, b in zip(res[0], res[2])) < 0.2, (res[0], res[2])
+
+
 def _with_dropout(name, p=0.1):
     import dataclasses
     return dataclasses.replace(get_config(name), dropout=p)

@@ -321,6 +321,34 @@ def test_gemm_fp8_delayed_scaling():
     assert rel < 6e-2, float(rel)
 
 
+def test_gemm_fp8_e5m2_dgrad_and_transposed_quantise():
+    """dgrad formulation: dX[M, K] = dY[M, N] (e5m2) @ W[N, K] with W held as the TRANSPOSED e4m3 copy W8T[K, N] produced
+    by quantize_fp8_t -- the byte-exact transpose of quantize_fp8(W) -- so both operands stay K-major for kind::f8f6f4."""
+    torch.manual_seed(14)
+    M, N, K = 1024, 1536, 768
+    dY, Wt = _bf(M, N, scale=3e-3), _bf(N, K, scale=0.05)
+    sd, sw = ops.Fp8Scale(DEV), ops.Fp8Scale(DEV)
+    d8 = torch.empty(M, N, device=DEV, dtype=torch.uint8)
+    w8, w8t = torch.empty(N, K, device=DEV, dtype=torch.uint8), torch.empty(K, N, device=DEV, dtype=torch.uint8)
+    for _ in range(2):
+        ops.quantize_fp8(dY, d8, sd, e5m2=True)
+        ops.quantize_fp8(Wt, w8, sw)
+        sd.scale.copy_(sd.amax / ops.E5M2_MAX); sd.amax.zero_()
+        sw.roll()
+    ops.quantize_fp8(dY, d8, sd, e5m2=True)
+    ops.quantize_fp8(Wt, w8, sw)
+    ops.quantize_fp8_t(Wt, w8t, sw)
+    assert torch.equal(w8t, w8.t().contiguous())
+    out = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_fp8(d8, w8t, out, sd, sw, a_e5m2=True)
+    Dd = d8.view(torch.float8_e5m2).float() * sd.scale
+    Wd = w8.view(torch.float8_e4m3fn).float() * sw.scale
+    _close(out, Dd @ Wd, rtol=1e-2)
+    exact = dY.float() @ Wt.float()
+    rel = (out.float() - exact).norm() / exact.norm()
+    assert rel < 0.12, float(rel)   # e5m2 keeps 2 mantissa bits: ~2^-3 worst-case per element, averaged down by the K sum
+
+
 def test_checksum_matches_cpu_and_detects_change():
     torch.manual_seed(13)
     x = torch.randn(256 * 37, device=DEV)
