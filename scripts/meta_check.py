@@ -57,7 +57,7 @@ def main():
     ex = PeerExchange(tr.man, delta_dtype=args.delta_dtype)
     r = 1
     ex.publish_delta(tr, r)
-    torch.cuda.synchronize()
+    barrier_sync(dev)  # fetch_delta below is the non-blocking host API (None until the peer's flag is up): publish everywhere first
     miners = list(range(world))
     K = args.steps
     out = {"world": world, "model": args.model, "val_batch": [Bv, Tv], "steps": K, "delta_dtype": args.delta_dtype, "modes": {}}

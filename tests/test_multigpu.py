@@ -15,13 +15,33 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+def _free_port() -> int:
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
+def _launch(tag, n, script, args=(), env=None, timeout=900):
+    """torchrun ``script`` on n local GPUs; the complete stdout / stderr goes to gpurun_out/multigpu_<tag>.log so that a failure
+    on a remote box can be read afterwards."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, script), *args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"multigpu_{tag}.log"), "w") as f:
+            f.write(f"rc={r.returncode}\n--- stdout ---\n{r.stdout[-20000:]}\n--- stderr ---\n{r.stderr[-20000:]}\n")
+    except OSError:
+        pass
+    return r
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_peer_exchange_matches_nccl_reference():
     n = min(_ngpu(), 4)
     env = dict(os.environ, PEER_CHECK_MB="8")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "scripts", "peer_check.py")],
-                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    r = _launch("peer_check", n, "scripts/peer_check.py", [], env=env, timeout=600)
     line = [l for l in r.stdout.splitlines() if l.startswith("PEER_CHECK ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(line[-1][len("PEER_CHECK "):])
@@ -30,10 +50,7 @@ def test_peer_exchange_matches_nccl_reference():
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_bench_two_gpus_runs():
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29612", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "6",
-                        "--warmup", "3", "--model", "gpt2-tiny", "--batch-size", "8", "--local-steps", "3"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _launch("bench", 2, "bench.py", ["--gpus", "2", "--steps", "6", "--warmup", "3", "--model", "gpt2-tiny", "--batch-size", "8", "--local-steps", "3"], timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])
@@ -45,9 +62,7 @@ def test_nvls_plane_matches_allreduce_reference():
     """In-switch reduction + multicast broadcast (multimem.*) == fp32 all-reduce reference; skipped where the box exposes no
     multicast object."""
     n = min(_ngpu(), 4)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "scripts", "nvls_check.py"), "--mb", "16"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _launch("nvls_check", n, "scripts/nvls_check.py", ["--mb", "16"], timeout=600)
     line = [l for l in r.stdout.splitlines() if l.startswith("NVLS_CHECK ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(line[-1][len("NVLS_CHECK "):])
@@ -61,10 +76,7 @@ def test_distributed_meta_learner_peer_vs_nccl_vs_sequential():
     """The sharded learned mixer over peer windows (csrc/meta_avg.cu) == its NCCL formulation == the sequential one-rank
     reference loop; w bit-identical on every rank."""
     n = min(_ngpu(), 4)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29614", os.path.join(ROOT, "scripts", "meta_check.py"), "--model", "gpt2-tiny",
-                        "--val-batch", "9", "--val-seq", "64", "--steps", "6"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = _launch("meta_check", n, "scripts/meta_check.py", ["--model", "gpt2-tiny", "--val-batch", "9", "--val-seq", "64", "--steps", "6"], timeout=900)
     line = [l for l in r.stdout.splitlines() if l.startswith("META_CHECK ")]
     assert line, r.stdout[-2000:] + r.stderr[-3000:]
     out = json.loads(line[-1][len("META_CHECK "):])
@@ -78,10 +90,7 @@ def test_collective_validator_matches_serial_scoring():
     """All ranks scoring the deltas together (large-batch, graph-captured EvalModel, verdicts from the publish flags) gives the
     same losses as the serial apply-then-evaluate validator and as the NCCL-broadcast baseline."""
     n = min(_ngpu(), 4)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29616", os.path.join(ROOT, "scripts", "validator_bench.py"), "--model", "gpt2-tiny",
-                        "--eval-seq", "64", "--eval-batches", "5", "--eval-rows", "20", "--miner-steps", "4"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = _launch("validator_bench", n, "scripts/validator_bench.py", ["--model", "gpt2-tiny", "--eval-seq", "64", "--eval-batches", "5", "--eval-rows", "20", "--miner-steps", "4"], timeout=900)
     line = [l for l in r.stdout.splitlines() if l.startswith("VALBENCH ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
     out = json.loads(line[-1][len("VALBENCH "):])
@@ -93,9 +102,7 @@ def test_collective_validator_matches_serial_scoring():
 def test_role_mode_peer_plane_averager_at_nonzero_rank():
     """Miners must see (and adopt) the base published by an averager that is NOT rank 0 (advisor finding of round 1)."""
     n = min(_ngpu(), 3)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "role_mode_check.py")],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _launch("role_mode_check", n, "scripts/role_mode_check.py", [], timeout=600)
     line = [l for l in r.stdout.splitlines() if l.startswith("ROLE_CHECK ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
     assert json.loads(line[-1][len("ROLE_CHECK "):])["ok"]
