@@ -88,10 +88,57 @@ DTB_DEVICE void tmem_ld32(uint32_t taddr, float* f) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
 }
+DTB_DEVICE void tmem_ld32x2(uint32_t ta, float* a, uint32_t tb, float* b) {
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(ta, ra);
+  tmem_ld_32x32b_x32(tb, rb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    a[i] = __uint_as_float(ra[i]);
+    b[i] = __uint_as_float(rb[i]);
+  }
+}
 // write 8 bf16 (16 B) of row `row`, logical 16B-chunk `ch` (0..7) into a [128 x 128 B] 128B-swizzled tile
 DTB_DEVICE void st_swz(uint8_t* tile, int row, int ch, uint4 v) {
   *reinterpret_cast<uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
 }
+
+// ---- softmax building blocks (one thread = one query row, 32-column chunks read from TMEM) -------------------------
+// ncu of the T = 512 kernels (profiles/ncu_r2_attn_tiled.md): 27 SASS instructions per score, 25 % issue utilisation at 2 warps
+// per scheduler -- per-element mask compares, the denormal-safe exp2f() expansion and serial max / sum chains.  Hence:
+// MUFU.EX2 directly, the mask as one 32-bit word per chunk (warp-uniform all / none fast paths), four independent chains.
+DTB_DEVICE float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bit i set  <=>  column ch * 32 + i is a valid key for this row (c_lo <= c <= c_hi)
+DTB_DEVICE uint32_t chunk_mask(int c_lo, int c_hi, int ch) {
+  const int lo = max(c_lo - ch * 32, 0), hi = min(c_hi - ch * 32, 31);
+  return lo > hi ? 0u : ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+}
+template <bool MASKED>
+DTB_DEVICE float chunk_rowmax(const float* s, uint32_t vm) {
+  float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+  for (int i = 0; i < 32; ++i) m[i & 3] = fmaxf(m[i & 3], (!MASKED || ((vm >> i) & 1u)) ? s[i] : -CUDART_INF_F);
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+// s[i] <- 2^(s[i] * sl2 - mref) (0 where masked); returns the chunk's sum
+template <bool MASKED>
+DTB_DEVICE float chunk_exp(float* s, uint32_t vm, float sl2, float mref) {
+  float l[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float e = ex2_fast(fmaf(s[i], sl2, -mref));
+    if (MASKED) e = ((vm >> i) & 1u) ? e : 0.f;
+    s[i] = e;
+    l[i & 3] += e;
+  }
+  return (l[0] + l[1]) + (l[2] + l[3]);
+}
+constexpr uint32_t kFullWarp = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward
@@ -188,31 +235,29 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     float mx = -CUDART_INF_F;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
+      const uint32_t vm = chunk_mask(c_lo, c_hi, ch);
+      if (!__any_sync(kFullWarp, vm != 0u)) continue;  // warp-uniform: tcgen05.ld is a warp-collective
       float s[32];
       tmem_ld32(tS + lane_off + ch * 32, s);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = ch * 32 + i;
-        if (c >= c_lo && c <= c_hi) mx = fmaxf(mx, s[i]);
-      }
+      mx = fmaxf(mx, __all_sync(kFullWarp, vm == kFullWarp) ? chunk_rowmax<false>(s, vm) : chunk_rowmax<true>(s, vm));
     }
     const float m_new = fmaxf(m_run, mx * sl2);
     const float m_ref = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-    const float alpha = exp2f(m_run - m_ref);  // m_run = -inf -> 0
+    const float alpha = ex2_fast(m_run - m_ref);  // m_run = -inf -> 0
     float lsum = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
+      const uint32_t vm = chunk_mask(c_lo, c_hi, ch);
+      uint8_t* atom = sP + (ch >> 1) * kTile;
+      if (!__any_sync(kFullWarp, vm != 0u)) {  // beyond the diagonal for every row of this warp: P = 0
+#pragma unroll
+        for (int v = 0; v < 4; ++v) st_swz(atom, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
+        continue;
+      }
       float s[32];
       tmem_ld32(tS + lane_off + ch * 32, s);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = ch * 32 + i;
-        const float e = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - m_ref) : 0.f;
-        s[i] = e;
-        lsum += e;
-      }
+      lsum += __all_sync(kFullWarp, vm == kFullWarp) ? chunk_exp<false>(s, vm, sl2, m_ref) : chunk_exp<true>(s, vm, sl2, m_ref);
       if (dthr) drop_p32(s, rowkey, k0 + ch * 32, dthr, p.drop.scale);
-      uint8_t* atom = sP + (ch >> 1) * kTile;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         uint4 q;
@@ -290,9 +335,12 @@ template <bool WRITE_P>
 DTB_DEVICE void bwd_softmax_tiles(uint32_t tS, uint32_t tDP, uint32_t lane_off, int tid, int c_lo, int c_hi, float sl2,
                                   float lse_l2, float Drow, float scale, uint8_t* sP, uint8_t* sDS, uint32_t rowkey, int k0,
                                   uint32_t dthr, float dscale, int ch_lo = 0, int ch_hi = 3) {
+  const float nD = -Drow * scale;
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
-    if (ch < ch_lo || ch > ch_hi) {  // warp-uniformly masked chunk (see attn_fwd_small_kernel): P = dS = 0
+    const uint32_t vm = chunk_mask(c_lo, c_hi, ch);
+    // warp-uniformly masked chunk (see attn_fwd_small_kernel; the vote also covers the tiled kernels' diagonal blocks): P = dS = 0
+    if (ch < ch_lo || ch > ch_hi || !__any_sync(kFullWarp, vm != 0u)) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         if (WRITE_P) st_swz(sP + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
@@ -301,8 +349,8 @@ DTB_DEVICE void bwd_softmax_tiles(uint32_t tS, uint32_t tDP, uint32_t lane_off, 
       continue;
     }
     float s[32], dp[32];
-    tmem_ld32(tS + lane_off + ch * 32, s);
-    tmem_ld32(tDP + lane_off + ch * 32, dp);
+    tmem_ld32x2(tS + lane_off + ch * 32, s, tDP + lane_off + ch * 32, dp);  // both loads in flight, one wait
+    const bool all = __all_sync(kFullWarp, vm == kFullWarp);
     if (dthr) {  // dropout on P: dV uses the masked P, dS = P * (mask * dP - D) * scale  (D = rowsum(dO * O) is unchanged)
       float mk[32];
 #pragma unroll
@@ -310,18 +358,24 @@ DTB_DEVICE void bwd_softmax_tiles(uint32_t tS, uint32_t tDP, uint32_t lane_off, 
       drop_p32(mk, rowkey, k0 + ch * 32, dthr, dscale);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int c = ch * 32 + i;
-        const float pv = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - lse_l2) : 0.f;
+        const float e = ex2_fast(fmaf(s[i], sl2, -lse_l2));
+        const float pv = (all || ((vm >> i) & 1u)) ? e : 0.f;
         s[i] = pv * mk[i];
-        dp[i] = pv * (dp[i] * mk[i] - Drow) * scale;
+        dp[i] = pv * fmaf(dp[i] * mk[i], scale, nD);
+      }
+    } else if (all) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float pv = ex2_fast(fmaf(s[i], sl2, -lse_l2));
+        s[i] = pv;
+        dp[i] = pv * fmaf(dp[i], scale, nD);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int c = ch * 32 + i;
-        const float pv = (c >= c_lo && c <= c_hi) ? exp2f(s[i] * sl2 - lse_l2) : 0.f;
+        const float pv = ((vm >> i) & 1u) ? ex2_fast(fmaf(s[i], sl2, -lse_l2)) : 0.f;
         s[i] = pv;
-        dp[i] = pv * (dp[i] - Drow) * scale;
+        dp[i] = pv * fmaf(dp[i], scale, nD);
       }
     }
 #pragma unroll
@@ -744,32 +798,25 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_small_kernel(const __grid_con
   float mx = -CUDART_INF_F;
 #pragma unroll 1
   for (int ch = ch_lo; ch <= ch_hi; ++ch) {
+    const uint32_t vm = chunk_mask(c_lo, c_hi, ch);
+    if (!__any_sync(kFullWarp, vm != 0u)) continue;
     float sv[32];
     tmem_ld32(tmem + lane_off + ch * 32, sv);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = ch * 32 + i;
-      if (c >= c_lo && c <= c_hi) mx = fmaxf(mx, sv[i]);
-    }
+    mx = fmaxf(mx, __all_sync(kFullWarp, vm == kFullWarp) ? chunk_rowmax<false>(sv, vm) : chunk_rowmax<true>(sv, vm));
   }
-  const float m_ref = mx * sl2;
+  const float m_ref = mx == -CUDART_INF_F ? 0.f : mx * sl2;  // fully masked row (rows >= M): P = 0, no NaN
   float lsum = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
-    if (ch < ch_lo || ch > ch_hi) {  // fully masked for this warp: P = 0
+    const uint32_t vm = chunk_mask(c_lo, c_hi, ch);
+    if (ch < ch_lo || ch > ch_hi || !__any_sync(kFullWarp, vm != 0u)) {  // fully masked for this warp: P = 0
 #pragma unroll
       for (int v = 0; v < 4; ++v) st_swz(sP + (ch >> 1) * kTile, tid, (ch & 1) * 4 + v, make_uint4(0, 0, 0, 0));
       continue;
     }
     float sv[32];
     tmem_ld32(tmem + lane_off + ch * 32, sv);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = ch * 32 + i;
-      const float e = (c >= c_lo && c <= c_hi) ? exp2f(sv[i] * sl2 - m_ref) : 0.f;
-      sv[i] = e;
-      lsum += e;
-    }
+    lsum += __all_sync(kFullWarp, vm == kFullWarp) ? chunk_exp<false>(sv, vm, sl2, m_ref) : chunk_exp<true>(sv, vm, sl2, m_ref);
     if (p.drop.thr) drop_p32(sv, rowkey, q0 + ch * 32, p.drop.thr, p.drop.scale);
     // all 128 threads finished READING Q/K? they are only read by the tensor core, which completed (bars[1]) -> safe
 #pragma unroll
