@@ -138,6 +138,22 @@ DTB_DEVICE float chunk_exp(float* s, uint32_t vm, float sl2, float mref) {
   }
   return (l[0] + l[1]) + (l[2] + l[3]);
 }
+// Longest-first CTA order for the tiled kernels.  Causal cost grows with the block's position inside its sequence (q-owner
+// CTAs: position + 1 kv blocks; kv-owner CTAs: blocks-per-sequence - position q blocks), and the grid is 1.3 - 2.6 waves, so
+// in natural order a 4-iteration CTA that starts in the tail sets the kernel time.  Linear CTA id (= dispatch order) ->
+// (block, head) with all heaviest blocks first.  Identity unless the batch is whole sequences of a multiple of 128 tokens.
+DTB_DEVICE void lpt_block(const AttnParams& p, bool heavy_last, int& blk, int& h) {
+  blk = blockIdx.x;
+  h = blockIdx.y;
+  const int nps = p.T / kBlk;
+  if (nps <= 1 || p.T % kBlk != 0 || p.M % p.T != 0) return;
+  const int heads = gridDim.y, per_class = (p.M / p.T) * heads;
+  const int L = blockIdx.y * gridDim.x + blockIdx.x;
+  const int cls = L / per_class, idx = L - cls * per_class;  // cls 0 = heaviest
+  h = idx % heads;
+  blk = (idx / heads) * nps + (heavy_last ? nps - 1 - cls : cls);
+}
+
 constexpr uint32_t kFullWarp = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -161,7 +177,8 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qb = blockIdx.x, h = blockIdx.y;
+  int qb, h;
+  lpt_block(p, true, qb, h);
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qb * kBlk;
   const int row_tok = q0 + tid;
@@ -460,7 +477,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kv_kernel(const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int kb = blockIdx.x, hk = blockIdx.y;
+  int kb, hk;
+  lpt_block(p, false, kb, hk);
   const int group = p.H / p.Hkv;
   const int k0 = kb * kBlk;
   // q blocks that can attend into this kv block: from kb up to the block holding the end of the last key's sequence
@@ -611,7 +629,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_q_kernel(const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qb = blockIdx.x, h = blockIdx.y;
+  int qb, h;
+  lpt_block(p, true, qb, h);
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qb * kBlk;
   const int row_tok = q0 + tid;
