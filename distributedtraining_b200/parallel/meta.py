@@ -24,7 +24,6 @@ the latter is the CPU/gloo test oracle and the NCCL baseline.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence
 
 import torch
