@@ -21,7 +21,7 @@ from .transformer import (ModelConfig, TransformerEngine, build_manifest, from_h
 class Trainer:
     def __init__(self, model="gpt2", device="cpu", batch: int = 1, seq: int = 64, lr: float = 5e-4, seed: int = 0,
                  betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0, use_graph: Optional[bool] = None,
-                 lm_chunk: int = 16384, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
+                 lm_chunk: int = 32768, init_flat: Optional[torch.Tensor] = None, fp8_forward: bool = False,
                  dropout: Optional[float] = None, meta_dropout: bool = False, dropout_seed: Optional[int] = None,
                  buffers: Optional[Dict[str, torch.Tensor]] = None, fp8_backward: bool = False):
         if isinstance(model, str) and os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):

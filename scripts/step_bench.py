@@ -12,7 +12,7 @@ ap.add_argument("--seq", type=int, default=64)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--no-graph", action="store_true")
-ap.add_argument("--lm-chunk", type=int, default=16384)
+ap.add_argument("--lm-chunk", type=int, default=32768)
 ap.add_argument("--fp8", action="store_true")
 ap.add_argument("--fp8-bwd", action="store_true")
 ap.add_argument("--dropout", type=float, default=None)
