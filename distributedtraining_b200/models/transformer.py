@@ -606,8 +606,7 @@ class TransformerEngine:
             if backward:
                 ops.gemm(lgv, P.wte, self.dxf[c0:c1], b_mn=True)  # dxf = dlogits @ wte
                 ops.gemm(lgv, self.xf[c0:c1], self.G.wte, a_mn=True, b_mn=True, accumulate=True)  # dwte += dlogits^T xf
-        torch.sum(self.losses, dim=0, out=self.loss)
-        self.loss.mul_(scale)
+        ops.loss_mean(self.losses, scale, self.loss)
 
     def persist_small_from_source(self) -> None:
         """Copy the non-matrix tensors (norms, biases, position table: < 1 % of the bytes) from the peer source."""
@@ -632,7 +631,7 @@ class TransformerEngine:
         cfg, P, G = self.cfg, self.P, self.G
         B, T, H, Hkv, hd = self.B, self.T, cfg.n_head, cfg.kv_heads, cfg.head_dim
         if zero_grad:
-            self.grads.zero_()
+            ops.zero_(self.grads)
         self.forward(train=dropout)
         self._lm_head(backward=True)
         # Residual-stream gradients ping-pong between dx / dx2.  Each norm backward also produces, on the same pass, what

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -319,6 +320,28 @@ def ce_fwd_bwd(logits, targets, V, losses, grad_scale):
        "ce_fwd_bwd")
     _tick()
     return losses
+
+
+_ATEN_SMALL = os.environ.get("DTB200_ATEN_SMALL", "0") == "1"  # A/B switch: ATen fill / sum instead of memset node / loss_mean_kernel
+
+
+def loss_mean(losses, scale: float, out):
+    """out[()] = scale * sum(losses): the step's mean loss in ONE deterministic launch (csrc/elementwise.cu loss_mean_kernel)."""
+    if not use_kernels(losses) or _ATEN_SMALL:
+        torch.sum(losses, dim=0, out=out)
+        return out.mul_(scale)
+    _c(_lib.lib().dtb_loss_mean(_lib.ptr(losses), losses.numel(), ctypes.c_float(scale), _lib.ptr(out), _lib.stream_ptr()), "loss_mean")
+    _tick()
+    return out
+
+
+def zero_(t):
+    """Stream-ordered memset (a memset node under graph capture) of a contiguous tensor."""
+    if not use_kernels(t) or _ATEN_SMALL:
+        return t.zero_()
+    assert t.is_contiguous()
+    _c(_lib.lib().dtb_zero(_lib.ptr(t), ctypes.c_size_t(t.numel() * t.element_size()), _lib.stream_ptr()), "zero")
+    return t
 
 
 def colsum(x, out):

@@ -349,6 +349,22 @@ def test_gemm_fp8_e5m2_dgrad_and_transposed_quantise():
     assert rel < 0.12, float(rel)   # e5m2 keeps 2 mantissa bits: ~2^-3 worst-case per element, averaged down by the K sum
 
 
+def test_loss_mean_and_memset_zero():
+    """The step's loss reduction (one deterministic block) and the memset-node zeroing that replaced the ATen kernels."""
+    torch.manual_seed(15)
+    for n in (1, 33, 4096, 32768, 40001):
+        x = torch.rand(n, device=DEV) * 11.0
+        out = torch.zeros((), device=DEV)
+        ops.loss_mean(x, 1.0 / n, out)
+        assert abs(out.item() - x.double().mean().item()) < 1e-5 * 11.0
+        out2 = torch.zeros((), device=DEV)
+        ops.loss_mean(x, 1.0 / n, out2)
+        assert out.item() == out2.item()  # fixed reduction order
+    g = torch.randn(1 << 20, device=DEV)
+    ops.zero_(g[1024:])
+    assert float(g[1024:].abs().max()) == 0.0 and float(g[:1024].abs().max()) > 0.0
+
+
 def test_checksum_matches_cpu_and_detects_change():
     torch.manual_seed(13)
     x = torch.randn(256 * 37, device=DEV)
