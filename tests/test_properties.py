@@ -105,3 +105,57 @@ def test_dropout_hash_golden_values():
     a = ref.drop_mult_attn((7, 1), 4, 0.1, 1, 8, 2, "cpu")
     assert (a == 0).nonzero().tolist() == [[0, 0, 0, 3], [0, 0, 2, 2], [0, 0, 2, 3], [0, 0, 3, 2], [0, 0, 4, 0], [0, 0, 6, 6],
                                             [0, 1, 0, 3], [0, 1, 2, 4], [0, 1, 2, 5], [0, 1, 4, 7], [0, 1, 5, 3], [0, 1, 7, 6]]
+
+
+# ---- attention kernel index arithmetic (csrc/sm100_attention.cu), mirrored in Python -------------------------------------
+def _chunk_mask(c_lo, c_hi, ch):
+    lo, hi = max(c_lo - ch * 32, 0), min(c_hi - ch * 32, 31)
+    return 0 if lo > hi else ((0xFFFFFFFF >> (31 - hi)) & ((0xFFFFFFFF << lo) & 0xFFFFFFFF))
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(-700, 300), st.integers(-700, 300), st.integers(0, 3))
+def test_attention_chunk_mask_equals_per_element_predicate(c_lo, c_hi, ch):
+    """chunk_mask(): bit i set <=> c_lo <= ch*32 + i <= c_hi -- the predicate the kernels evaluated per element before."""
+    vm = _chunk_mask(c_lo, c_hi, ch)
+    for i in range(32):
+        assert ((vm >> i) & 1) == int(c_lo <= ch * 32 + i <= c_hi)
+
+
+def _lpt_block(L, grid_x, heads, T, M, heavy_last):
+    nps = T // 128
+    if nps <= 1 or T % 128 or M % T:
+        return L % grid_x, L // grid_x
+    per_class = (M // T) * heads
+    cls, idx = divmod(L, per_class)
+    return (idx // heads) * nps + (nps - 1 - cls if heavy_last else cls), idx % heads
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 6), st.sampled_from([64, 128, 256, 512, 1024]), st.integers(1, 12), st.booleans())
+def test_attention_lpt_order_is_a_permutation_with_heaviest_blocks_first(nseq, T, heads, heavy_last):
+    """lpt_block(): every (block, head) pair is visited exactly once, and the causal cost of the visited blocks never increases."""
+    M = nseq * T
+    grid_x = (M + 127) // 128
+    seen, costs = set(), []
+    for L in range(grid_x * heads):
+        blk, h = _lpt_block(L, grid_x, heads, T, M, heavy_last)
+        assert 0 <= blk < grid_x and 0 <= h < heads
+        seen.add((blk, h))
+        if T > 128:
+            pos = blk % (T // 128)
+            costs.append(pos + 1 if heavy_last else T // 128 - pos)
+    assert len(seen) == grid_x * heads
+    assert costs == sorted(costs, reverse=True)
+
+
+def test_loss_mean_and_zero_cpu_fallbacks():
+    import torch
+    from distributedtraining_b200 import ops
+    x = torch.arange(1, 11, dtype=torch.float32)
+    out = torch.zeros(())
+    ops.loss_mean(x, 0.1, out)
+    assert abs(out.item() - 5.5) < 1e-6
+    g = torch.ones(16)
+    ops.zero_(g)
+    assert float(g.abs().sum()) == 0.0
